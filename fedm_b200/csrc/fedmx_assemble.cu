@@ -1,0 +1,476 @@
+// Residual / Jacobian assembly for node-interleaved mixed P1 spaces on triangles (sm_100a).
+//
+// Replaces, for the FEDM form family, what FFC's generated tabulate_tensor kernels + dolfin's Assembler +
+// DirichletBC::apply do behind `Problem.F` / `Problem.J` (reference: fedm/functions.py:188-202).
+//
+// Design (HBM-bound FP64 work, no tensor cores): one thread owns one block row (mesh node).  It walks the
+// node's cell fan (consecutive cells share an edge); for every cell it evaluates row `a` of the element
+// tensor -- the residual entries R_a[k] and the three n_eq x n_eq blocks J[a][a], J[a][p], J[a][n] --
+// entirely in registers.  The block of an interior edge (i,j) is the sum of exactly two consecutive cells
+// of the fan, so it is finished in registers ("carry") and written ONCE, in a fixed order: the scatter-add is
+// deterministic by construction and every CSR value costs 8 bytes of DRAM write traffic, no atomics, no
+// read-modify-write (except one L2-resident wrap-around block per interior node).
+// Storage is SELL-32 with entry-major groups (fedmx_internal.h): the 32 lanes of a warp own 32 consecutive
+// rows, so every store instruction writes 256 contiguous bytes.
+// Dirichlet rows are fused into the epilogue: b_i = x_i - g, Jacobian row = unit row (pattern kept).
+#include <math.h>
+
+#include "fedmx_internal.h"
+
+namespace {
+
+constexpr double kTwoPi = 6.283185307179586476925286766559;
+
+// Gauss-Legendre nodes on [0,1]
+__device__ __constant__ double kGL2_t[2] = {0.21132486540518711775, 0.78867513459481288225};
+__device__ __constant__ double kGL3_t[3] = {0.11270166537925831148, 0.5, 0.88729833462074168852};
+__device__ __constant__ double kGL3_w[3] = {0.27777777777777777778, 0.44444444444444444444, 0.27777777777777777778};
+
+struct AsmArgs {
+    SellView S;
+    const double *coords;   // [n_vertices][2]
+    const double *x;        // [n_vertices][n_eq]
+    const double *fields;   // [n_vertices][n_fields]
+    double *val;            // matrix values (may be null for residual-only)
+    double *res;            // residual (may be null)
+    ModelParams mp;
+};
+
+// One vertex as seen by a model: coordinates, unknowns, coefficient fields.
+template <int NEQ, int NF>
+struct Vtx {
+    double r, z;
+    double u[NEQ];
+    double f[NF > 0 ? NF : 1];
+};
+
+template <int NEQ, int NF>
+__device__ __forceinline__ void load_vertex(const AsmArgs &A, int32_t v, Vtx<NEQ, NF> &o) {
+    const double2 c = *reinterpret_cast<const double2 *>(A.coords + 2 * int64_t(v));
+    o.r = c.x;
+    o.z = c.y;
+#pragma unroll
+    for (int k = 0; k < NEQ; ++k) o.u[k] = __ldg(A.x + int64_t(NEQ) * v + k);
+#pragma unroll
+    for (int k = 0; k < NF; ++k) o.f[k] = __ldg(A.fields + int64_t(NF) * v + k);
+}
+
+// Row `a` of one element tensor, local vertex order (a, p, n) = (0, 1, 2).
+template <int NEQ>
+struct RowOut {
+    double R[NEQ];
+    double J[3][NEQ * NEQ];   // J[b][k*NEQ + l] = d R_a[k] / d U_b[l]
+};
+
+// =====================================================================================================
+// Streamer model (LFA, N_eq = 3: ln n_i, ln n_e, Phi).
+// Reference: tests/integrated_tests/streamer_discharge/fedm_streamer.py:243-279 (coefficients, fluxes, sources,
+// balance equations, Poisson, Neumann drift flux on the electrodes) over fedm/functions.py:219-237, 350-368,
+// 401, 523-524.  Closed form: SURVEY.md Appendix A.  Quadrature: degree 2 (3-point) on cells, 2-point
+// Gauss-Legendre on facets (parameters["form_compiler"]["quadrature_degree"] = 2, fedm_streamer.py:29).
+// params: [0]=mu_c [1]=mu_p [2]=D_c [3]=D_p [4]=a_c1 [5]=a_c2 [6]=a_c4 [7]=a_c3 [8]=e/eps0
+//         [9]=bitmask of facet markers carrying the electron 'Neumann' drift flux
+// fields: [0]=hist_i [1]=hist_e  (BDF2 history, fedmx_bdf2_history)
+// =====================================================================================================
+struct StreamerModel {
+    static constexpr int NEQ = 3;
+    static constexpr int NF = 2;
+
+    template <bool JAC>
+    static __device__ __forceinline__ void row(const ModelParams &mp, const Vtx<3, 2> &a, const Vtx<3, 2> &p,
+                                               const Vtx<3, 2> &n, uint32_t mk_ap, uint32_t mk_an,
+                                               RowOut<3> &o) {
+        // --- geometry (fedm uses x[0] = r, x[1] = z)
+        const double e1r = p.r - a.r, e1z = p.z - a.z, e2r = n.r - a.r, e2z = n.z - a.z;
+        const double det = e1r * e2z - e1z * e2r;
+        const double inv = 1.0 / det;
+        const double gpr = e2z * inv, gpz = -e2r * inv;
+        const double gnr = -e1z * inv, gnz = e1r * inv;
+        const double gar = -gpr - gnr, gaz = -gpz - gnz;
+        const double gr[3] = {gar, gpr, gnr}, gz[3] = {gaz, gpz, gnz};
+        const double adet = fabs(det);
+        // --- cell-constant fields
+        const double Gr = a.u[2] * gar + p.u[2] * gpr + n.u[2] * gnr;
+        const double Gz = a.u[2] * gaz + p.u[2] * gpz + n.u[2] * gnz;
+        const double Hr = a.u[1] * gar + p.u[1] * gpr + n.u[1] * gnr;
+        const double Hz = a.u[1] * gaz + p.u[1] * gpz + n.u[1] * gnz;
+        const double Em = sqrt(Gr * Gr + Gz * Gz);
+        const double iEm = 1.0 / Em;
+        const double lnE = log(Em);
+        const double mu = mp.p[0] * exp(mp.p[1] * lnE);
+        const double D = mp.p[2] * exp(mp.p[3] * lnE);
+        const double iE3 = iEm * iEm * iEm;
+        const double ex = exp(-mp.p[6] * iEm);
+        const double pre = mp.p[4] + mp.p[5] * iE3;
+        const double alpha = pre * ex - mp.p[7];
+        const double S = alpha * mu * Em;
+        const double kappa = mp.p[8];
+        const double tr = mp.dt / mp.dt_old;
+        const double ct = (1.0 + 2.0 * tr) / ((1.0 + tr) * mp.dt);
+        // drift-diffusion vector P = -D H + mu G   (Gamma = n_e P)
+        const double Pr = -D * Hr + mu * Gr, Pz = -D * Hz + mu * Gz;
+        const double Pga = Pr * gar + Pz * gaz;
+        double dmu = 0, dD = 0, dS = 0;
+        if (JAC) {
+            dmu = mp.p[1] * mu * iEm;
+            dD = mp.p[3] * D * iEm;
+            const double dalpha = (-3.0 * mp.p[5] * iE3 * iEm + pre * mp.p[6] * iEm * iEm) * ex;
+            dS = dalpha * mu * Em + alpha * dmu * Em + alpha * mu;
+        }
+        // --- quadrature moments: q-th point has lambda = 2/3 at local vertex q and 1/6 elsewhere
+        double Ri = 0, Re = 0, Rphi_s = 0, Wsum = 0, Mne0 = 0, Mne = 0;
+        double Mii[3] = {0, 0, 0}, Mne2[3] = {0, 0, 0}, Mee[3] = {0, 0, 0}, Mni2[3] = {0, 0, 0}, Nb[3] = {0, 0, 0};
+        const double w0 = adet * (1.0 / 6.0) * kTwoPi;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const double l0 = (q == 0) ? (2.0 / 3.0) : (1.0 / 6.0);
+            const double l1 = (q == 1) ? (2.0 / 3.0) : (1.0 / 6.0);
+            const double l2 = (q == 2) ? (2.0 / 3.0) : (1.0 / 6.0);
+            const double rq = l0 * a.r + l1 * p.r + l2 * n.r;
+            const double W = w0 * rq;
+            const double ui = l0 * a.u[0] + l1 * p.u[0] + l2 * n.u[0];
+            const double ue = l0 * a.u[1] + l1 * p.u[1] + l2 * n.u[1];
+            const double hi = l0 * a.f[0] + l1 * p.f[0] + l2 * n.f[0];
+            const double he = l0 * a.f[1] + l1 * p.f[1] + l2 * n.f[1];
+            const double ni = exp(ui), ne = exp(ue);
+            const double bi = ct * ui + hi, be = ct * ue + he;
+            const double Wni = W * ni, Wne = W * ne;
+            Ri += (Wni * bi - S * Wne) * l0;
+            Re += (Wne * be - S * Wne) * l0;
+            Rphi_s += (Wni - Wne) * l0;
+            Wsum += W;
+            Mne += Wne;
+            if (JAC) {
+                Mne0 += Wne * l0;
+                const double lb[3] = {l0, l1, l2};
+                const double ti = Wni * (bi + ct) * l0, te = (Wne * (be + ct) - S * Wne) * l0;
+                const double tn = Wne * l0, tni = Wni * l0;
+#pragma unroll
+                for (int b = 0; b < 3; ++b) {
+                    Mii[b] += ti * lb[b];
+                    Mee[b] += te * lb[b];
+                    Mne2[b] += tn * lb[b];
+                    Mni2[b] += tni * lb[b];
+                    Nb[b] += Wne * lb[b];
+                }
+            }
+        }
+        o.R[0] = Ri;
+        o.R[1] = Re - Mne * Pga;
+        o.R[2] = Wsum * (Gr * gar + Gz * gaz) - kappa * Rphi_s;
+        if (JAC) {
+            const double Qr = -dD * Hr + dmu * Gr, Qz = -dD * Hz + dmu * Gz;   // dP/dEm
+            const double Qga = Qr * gar + Qz * gaz;
+#pragma unroll
+            for (int b = 0; b < 3; ++b) {
+                double *J = o.J[b];
+                const double Ghb = (Gr * gr[b] + Gz * gz[b]) * iEm;   // dEm/dPhi_b
+                const double gbga = gr[b] * gar + gz[b] * gaz;
+                J[0] = Mii[b];                       // d R_i / d U_i
+                J[1] = -S * Mne2[b];                 // d R_i / d U_e
+                J[2] = -dS * Ghb * Mne0;             // d R_i / d Phi
+                J[3] = 0.0;                          // d R_e / d U_i (stored: dolfin keeps the block)
+                J[4] = Mee[b];
+                J[5] = -dS * Ghb * Mne0 - Mne * (Qga * Ghb + mu * gbga);
+                J[6] = -kappa * Mni2[b];
+                J[7] = kappa * Mne2[b];
+                J[8] = Wsum * gbga;
+                // diffusion and drift parts of d R_e / d U_e :  + n_e D g_b.g_a  - n_e lambda_b P.g_a
+                J[4] += Mne * D * gbga - Nb[b] * Pga;
+            }
+        }
+        // --- exterior facets (a,p) and (a,n): 'Neumann' drift flux  2 pi r (-mu)(E.n) n_e v,  E = -G
+        const uint32_t mask = uint32_t(mp.p[9]);
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+            const uint32_t mk = side == 0 ? mk_ap : mk_an;
+            if (mk == 0 || !((mask >> mk) & 1u)) continue;
+            const Vtx<3, 2> &b = side == 0 ? p : n;        // other facet vertex
+            const Vtx<3, 2> &c = side == 0 ? n : p;        // opposite vertex
+            const int lb = side == 0 ? 1 : 2;
+            double tr_ = b.r - a.r, tz_ = b.z - a.z;
+            const double L = sqrt(tr_ * tr_ + tz_ * tz_);
+            double nr = tz_ / L, nz = -tr_ / L;
+            if (nr * (c.r - a.r) + nz * (c.z - a.z) > 0.0) { nr = -nr; nz = -nz; }
+            const double Gn = Gr * nr + Gz * nz;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const double t = kGL2_t[q];
+                const double la = 1.0 - t;
+                const double rq = la * a.r + t * b.r;
+                const double ne = exp(la * a.u[1] + t * b.u[1]);
+                const double W = 0.5 * L * kTwoPi * rq * ne * la;     // weight * n_e * test function
+                o.R[1] += W * mu * Gn;
+                if (JAC) {
+                    o.J[0][4] += W * mu * Gn * la;
+                    o.J[lb][4] += W * mu * Gn * t;
+#pragma unroll
+                    for (int bb = 0; bb < 3; ++bb) {
+                        const double Ghb = (Gr * gr[bb] + Gz * gz[bb]) * iEm;
+                        o.J[bb][5] += W * (dmu * Ghb * Gn + mu * (gr[bb] * nr + gz[bb] * nz));
+                    }
+                }
+            }
+        }
+    }
+};
+
+// =====================================================================================================
+// Poisson model (N_eq = 1): 2 pi r (grad u . grad v - f v) dx with f = kappa (exp(f0) - exp(f1)), f0/f1 P1
+// log-density fields.  Reference: weak_form_Poisson_equation (fedm/functions.py:379-401) as used for the
+// initial potential, fedm_streamer.py:210-223.  params: [0] = kappa = e/eps0.  Degree-2 quadrature.
+// =====================================================================================================
+struct PoissonModel {
+    static constexpr int NEQ = 1;
+    static constexpr int NF = 2;
+
+    template <bool JAC>
+    static __device__ __forceinline__ void row(const ModelParams &mp, const Vtx<1, 2> &a, const Vtx<1, 2> &p,
+                                               const Vtx<1, 2> &n, uint32_t, uint32_t, RowOut<1> &o) {
+        const double e1r = p.r - a.r, e1z = p.z - a.z, e2r = n.r - a.r, e2z = n.z - a.z;
+        const double det = e1r * e2z - e1z * e2r;
+        const double inv = 1.0 / det;
+        const double gpr = e2z * inv, gpz = -e2r * inv;
+        const double gnr = -e1z * inv, gnz = e1r * inv;
+        const double gar = -gpr - gnr, gaz = -gpz - gnz;
+        const double Gr = a.u[0] * gar + p.u[0] * gpr + n.u[0] * gnr;
+        const double Gz = a.u[0] * gaz + p.u[0] * gpz + n.u[0] * gnz;
+        const double w0 = fabs(det) * (1.0 / 6.0) * kTwoPi;
+        double Wsum = 0, src = 0;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const double l0 = (q == 0) ? (2.0 / 3.0) : (1.0 / 6.0);
+            const double l1 = (q == 1) ? (2.0 / 3.0) : (1.0 / 6.0);
+            const double l2 = (q == 2) ? (2.0 / 3.0) : (1.0 / 6.0);
+            const double W = w0 * (l0 * a.r + l1 * p.r + l2 * n.r);
+            const double f0 = l0 * a.f[0] + l1 * p.f[0] + l2 * n.f[0];
+            const double f1 = l0 * a.f[1] + l1 * p.f[1] + l2 * n.f[1];
+            Wsum += W;
+            src += W * (exp(f0) - exp(f1)) * l0;
+        }
+        o.R[0] = Wsum * (Gr * gar + Gz * gaz) - mp.p[0] * src;
+        if (JAC) {
+            o.J[0][0] = Wsum * (gar * gar + gaz * gaz);
+            o.J[1][0] = Wsum * (gpr * gar + gpz * gaz);
+            o.J[2][0] = Wsum * (gnr * gar + gnz * gaz);
+        }
+    }
+};
+
+// =====================================================================================================
+// Generic row kernel
+// =====================================================================================================
+template <int NB>
+__device__ __forceinline__ void store_block(double *val, int64_t group_base, int slot, int lane, const double *blk) {
+    double *dst = val + (group_base + int64_t(slot) * FEDMX_SLICE) * NB + lane;
+#pragma unroll
+    for (int e = 0; e < NB; ++e) dst[e * FEDMX_SLICE] = blk[e];
+}
+
+template <int NB>
+__device__ __forceinline__ void add_block(double *val, int64_t group_base, int slot, int lane, const double *blk) {
+    double *dst = val + (group_base + int64_t(slot) * FEDMX_SLICE) * NB + lane;
+#pragma unroll
+    for (int e = 0; e < NB; ++e) dst[e * FEDMX_SLICE] += blk[e];
+}
+
+template <class Model, bool JAC>
+__global__ void __launch_bounds__(128) assemble_rows_kernel(AsmArgs A) {
+    constexpr int NEQ = Model::NEQ, NF = Model::NF, NB = NEQ * NEQ;
+    const int64_t row = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t s = row / FEDMX_SLICE;
+    const int lane = int(row % FEDMX_SLICE);
+    if (s >= A.S.n_slices) return;
+    const bool active = row < A.S.n_rows;
+    const uint32_t rp = A.S.row_pack[row];
+    const int n_inc = active ? int(rp & 0xffu) : 0;
+    const int diag_slot = int((rp >> 8) & 0xffu);
+    const int bc = int(rp >> 16);                   // value index + 1, 0 = unconstrained
+    const int bc_comp = A.mp.bc_comp;
+    const int64_t gbase = A.S.slice_ptr[s];
+    const int64_t ibase = A.S.inc_ptr[s];
+    const int width = A.S.inc_width[s];
+
+    Vtx<NEQ, NF> va;
+    if (active) load_vertex<NEQ, NF>(A, int32_t(row), va);
+
+    double diag[NB], carry[NB], R[NEQ];
+#pragma unroll
+    for (int e = 0; e < NB; ++e) { diag[e] = 0.0; carry[e] = 0.0; }
+#pragma unroll
+    for (int k = 0; k < NEQ; ++k) R[k] = 0.0;
+
+    for (int m = 0; m < width; ++m) {
+        if (m >= n_inc) continue;
+        const int64_t e = ibase + int64_t(m) * FEDMX_SLICE + lane;
+        const int32_t vp = A.S.inc_vp[e], vn = A.S.inc_vn[e];
+        const uint32_t pack = A.S.inc_pack[e];
+        Vtx<NEQ, NF> p, n;
+        load_vertex<NEQ, NF>(A, vp, p);
+        load_vertex<NEQ, NF>(A, vn, n);
+        RowOut<NEQ> o;
+        Model::template row<JAC>(A.mp, va, p, n, PACK_MK_N(pack), PACK_MK_P(pack), o);
+#pragma unroll
+        for (int k = 0; k < NEQ; ++k) R[k] += o.R[k];
+        if (JAC) {
+#pragma unroll
+            for (int q = 0; q < NB; ++q) diag[q] += o.J[0][q];
+            if (PACK_FIRST(pack)) {
+#pragma unroll
+                for (int q = 0; q < NB; ++q) carry[q] = 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < NB; ++q) carry[q] += o.J[1][q];
+            if (bc) {
+#pragma unroll
+                for (int l = 0; l < NEQ; ++l) carry[bc_comp * NEQ + l] = 0.0;
+            }
+            // block (i, vp) is complete (or the partial first block of a closed fan): write it
+            store_block<NB>(A.val, gbase, PACK_SLOT_P(pack), lane, carry);
+#pragma unroll
+            for (int q = 0; q < NB; ++q) carry[q] = o.J[2][q];
+            if (PACK_LAST(pack)) {
+                if (bc) {
+#pragma unroll
+                    for (int l = 0; l < NEQ; ++l) carry[bc_comp * NEQ + l] = 0.0;
+                }
+                if (PACK_CLOSED(pack)) add_block<NB>(A.val, gbase, PACK_SLOT_N(pack), lane, carry);
+                else store_block<NB>(A.val, gbase, PACK_SLOT_N(pack), lane, carry);
+            }
+        }
+    }
+    if (!active) return;
+    if (bc) {
+        R[bc_comp] = va.u[bc_comp] - A.mp.bc_values[bc - 1];
+        if (JAC) {
+#pragma unroll
+            for (int l = 0; l < NEQ; ++l) diag[bc_comp * NEQ + l] = (l == bc_comp) ? 1.0 : 0.0;
+        }
+    }
+    if (JAC) store_block<NB>(A.val, gbase, diag_slot, lane, diag);
+    if (A.res) {
+#pragma unroll
+        for (int k = 0; k < NEQ; ++k) A.res[int64_t(NEQ) * row + k] = R[k];
+    }
+}
+
+__global__ void bdf2_history_kernel(int64_t n_nodes, int n_eq, int n_hist, const double *__restrict__ x_old,
+                                    const double *__restrict__ x_old1, double c_old, double c_old1,
+                                    double *__restrict__ fields, int n_fields, int field_offset) {
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n_nodes * n_hist) return;
+    const int64_t v = i / n_hist;
+    const int k = int(i % n_hist);
+    fields[v * n_fields + field_offset + k] = c_old * x_old[v * n_eq + k] + c_old1 * x_old1[v * n_eq + k];
+}
+
+template <class Model>
+int launch_assembly(fedmx_ctx *ctx, const double *d_x, double *d_b, bool jac) {
+    AsmArgs A;
+    A.S = ctx->sell;
+    A.coords = ctx->d_coords;
+    A.x = d_x;
+    A.fields = ctx->d_fields;
+    A.val = jac ? ctx->d_val : nullptr;
+    A.res = d_b;
+    A.mp = ctx->mp;
+    const int threads = 128;
+    const int64_t rows = ctx->sell.n_slices * FEDMX_SLICE;
+    const unsigned blocks = unsigned((rows + threads - 1) / threads);
+    if (jac) assemble_rows_kernel<Model, true><<<blocks, threads, 0, ctx->stream>>>(A);
+    else assemble_rows_kernel<Model, false><<<blocks, threads, 0, ctx->stream>>>(A);
+    ctx->launches++;
+    FEDMX_CHECK_CUDA(ctx, cudaGetLastError());
+    return FEDMX_OK;
+}
+
+int assemble_dispatch(fedmx_ctx *ctx, const double *d_x, double dt, double dt_old, double t,
+                      const double *h_bc_values, int n_bc_values, double *d_b, bool jac) {
+    FEDMX_REQUIRE(ctx, ctx->n_vertices > 0, "assemble: no mesh");
+    FEDMX_REQUIRE(ctx, ctx->mp.model_id != 0, "assemble: no model");
+    FEDMX_REQUIRE(ctx, d_x != nullptr, "assemble: null state");
+    FEDMX_REQUIRE(ctx, n_bc_values >= 0 && n_bc_values < FEDMX_MAX_BC, "assemble: too many Dirichlet values");
+    FEDMX_REQUIRE(ctx, ctx->mp.n_fields == 0 || ctx->d_fields, "assemble: coefficient fields not bound");
+    ctx->mp.dt = dt;
+    ctx->mp.dt_old = dt_old;
+    ctx->mp.t = t;
+    ctx->mp.bc_comp = ctx->bc_comp;
+    for (int i = 0; i < n_bc_values; ++i) ctx->mp.bc_values[i] = h_bc_values[i];
+    switch (ctx->mp.model_id) {
+        case FEDMX_MODEL_STREAMER:
+            return launch_assembly<StreamerModel>(ctx, d_x, d_b, jac);
+        case FEDMX_MODEL_POISSON:
+            return launch_assembly<PoissonModel>(ctx, d_x, d_b, jac);
+        default:
+            ctx->err = "assemble: model not implemented";
+            return FEDMX_EUNSUPPORTED;
+    }
+}
+
+}  // namespace
+
+int fedmx_assemble_internal(fedmx_ctx *ctx, const double *d_x, double dt, double dt_old, double t,
+                            const double *h_bc_values, int n_bc_values, double *d_b, bool jac) {
+    return assemble_dispatch(ctx, d_x, dt, dt_old, t, h_bc_values, n_bc_values, d_b, jac);
+}
+
+extern "C" int fedmx_model_set(fedmx_ctx *ctx, int model_id, int n_params, const double *h_params) {
+    if (!ctx) return FEDMX_EINVAL;
+    FEDMX_REQUIRE(ctx, n_params >= 0 && n_params <= FEDMX_MAX_PARAMS, "fedmx_model_set: too many parameters");
+    int neq = 0, nf = 0;
+    switch (model_id) {
+        case FEDMX_MODEL_STREAMER: neq = StreamerModel::NEQ; nf = StreamerModel::NF; break;
+        case FEDMX_MODEL_POISSON: neq = PoissonModel::NEQ; nf = PoissonModel::NF; break;
+        default:
+            ctx->err = "fedmx_model_set: unknown model id";
+            return FEDMX_EUNSUPPORTED;
+    }
+    FEDMX_REQUIRE(ctx, ctx->n_eq == 0 || ctx->n_eq == neq, "fedmx_model_set: n_eq of mesh and model differ");
+    ctx->mp.model_id = model_id;
+    ctx->mp.n_eq = neq;
+    ctx->mp.n_fields = nf;
+    for (int i = 0; i < FEDMX_MAX_PARAMS; ++i) ctx->mp.p[i] = i < n_params ? h_params[i] : 0.0;
+    return FEDMX_OK;
+}
+
+extern "C" int fedmx_fields_bind(fedmx_ctx *ctx, int n_fields, const double *d_fields) {
+    if (!ctx) return FEDMX_EINVAL;
+    FEDMX_REQUIRE(ctx, ctx->mp.model_id != 0, "fedmx_fields_bind: set the model first");
+    FEDMX_REQUIRE(ctx, n_fields == ctx->mp.n_fields, "fedmx_fields_bind: wrong number of fields for this model");
+    ctx->d_fields = d_fields;
+    return FEDMX_OK;
+}
+
+extern "C" int fedmx_assemble_residual(fedmx_ctx *ctx, const double *d_x, double dt, double dt_old, double t,
+                                       const double *h_bc_values, int n_bc_values, double *d_b) {
+    if (!ctx) return FEDMX_EINVAL;
+    FEDMX_REQUIRE(ctx, d_b != nullptr, "fedmx_assemble_residual: null output");
+    return assemble_dispatch(ctx, d_x, dt, dt_old, t, h_bc_values, n_bc_values, d_b, false);
+}
+
+extern "C" int fedmx_assemble_jacobian(fedmx_ctx *ctx, const double *d_x, double dt, double dt_old, double t,
+                                       const double *h_bc_values, int n_bc_values, double *d_b) {
+    if (!ctx) return FEDMX_EINVAL;
+    int rc = assemble_dispatch(ctx, d_x, dt, dt_old, t, h_bc_values, n_bc_values, d_b, true);
+    if (rc) return rc;
+    return fedmx_update_block_jacobi(ctx);
+}
+
+extern "C" int fedmx_bdf2_history(fedmx_ctx *ctx, int n_hist, const double *d_x_old, const double *d_x_old1,
+                                  double dt, double dt_old, double *d_fields, int n_fields, int field_offset) {
+    if (!ctx) return FEDMX_EINVAL;
+    FEDMX_REQUIRE(ctx, ctx->n_vertices > 0, "fedmx_bdf2_history: no mesh");
+    FEDMX_REQUIRE(ctx, n_hist > 0 && n_hist <= ctx->n_eq && field_offset >= 0 && field_offset + n_hist <= n_fields,
+                  "fedmx_bdf2_history: bad field layout");
+    const double tr = dt / dt_old;
+    const double trp1 = 1.0 + tr;
+    const double c_old = -(trp1 * trp1) / (trp1 * dt);
+    const double c_old1 = (tr * tr) / (trp1 * dt);
+    const int64_t n = ctx->n_vertices * n_hist;
+    const int threads = 256;
+    bdf2_history_kernel<<<unsigned((n + threads - 1) / threads), threads, 0, ctx->stream>>>(
+        ctx->n_vertices, ctx->n_eq, n_hist, d_x_old, d_x_old1, c_old, c_old1, d_fields, n_fields, field_offset);
+    ctx->launches++;
+    FEDMX_CHECK_CUDA(ctx, cudaGetLastError());
+    return FEDMX_OK;
+}

@@ -1,0 +1,65 @@
+// Context life cycle, error reporting, host-side step-size controllers.
+#include <math.h>
+
+#include "fedmx_internal.h"
+
+extern "C" const char *fedmx_version(void) { return "fedmx 0.1 (sm_100a)"; }
+
+extern "C" int fedmx_ctx_create(int device, fedmx_ctx **out) {
+    if (!out) return FEDMX_EINVAL;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || device < 0 || device >= count) return FEDMX_ECUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return FEDMX_ECUDA;
+    fedmx_ctx *ctx = new fedmx_ctx();
+    ctx->device = device;
+    ctx->mp = ModelParams{};
+    ctx->mp.bc_comp = -1;
+    *out = ctx;
+    return FEDMX_OK;
+}
+
+extern "C" int fedmx_ctx_destroy(fedmx_ctx *ctx) {
+    if (!ctx) return FEDMX_EINVAL;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (void *p : ctx->owned_device) cudaFree(p);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    delete ctx;
+    return FEDMX_OK;
+}
+
+extern "C" const char *fedmx_last_error(const fedmx_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" int fedmx_set_stream(fedmx_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return FEDMX_EINVAL;
+    ctx->stream = (cudaStream_t)cuda_stream;
+    return FEDMX_OK;
+}
+
+extern "C" int64_t fedmx_launch_count(fedmx_ctx *ctx, int reset) {
+    if (!ctx) return -1;
+    int64_t n = ctx->launches;
+    if (reset) ctx->launches = 0;
+    return n;
+}
+
+// Step-size controllers: plain libm pow() so that the dt sequence is bit-identical to the reference's
+// Python floats (reference: fedm/functions.py:915-951; pinned by the golden relative-error logs).
+static double clampd(double dt, double dt_min, double dt_max) { return fmax(fmin(dt, dt_max), dt_min); }
+
+extern "C" double fedmx_pid_step(double dt, const double err[3], double tol, double dt_min, double dt_max) {
+    dt *= pow(err[1] / err[0], 0.075) * pow(tol / err[0], 0.175) * pow(err[1] * err[1] / (err[0] * err[2]), 0.01);
+    return clampd(dt, dt_min, dt_max);
+}
+
+extern "C" double fedmx_pi34_step(double dt, const double err[3], double tol, double dt_min, double dt_max) {
+    dt *= pow(0.8 * tol / err[0], 0.3 / 3) * pow(0.8 * err[1] / err[0], 0.4 / 3);
+    return clampd(dt, dt_min, dt_max);
+}
+
+extern "C" double fedmx_h211b_step(double dt, double dt_old, const double err[3], double tol, double dt_min, double dt_max) {
+    dt *= pow(0.8 * tol / err[0], 1.0 / 12) * pow(0.8 * tol / err[1], 1.0 / 12) * pow(dt / dt_old, -1.0 / 4);
+    return clampd(dt, dt_min, dt_max);
+}

@@ -1,0 +1,144 @@
+// Internal declarations of libfedmx (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/fedmx.h"
+
+#define FEDMX_MAX_EQ 5
+#define FEDMX_MAX_PARAMS 64
+#define FEDMX_MAX_BC 16
+#define FEDMX_SLICE 32
+
+// Device-side view of the mesh topology in SELL-32 (sliced ELLPACK, 32 rows per slice) form.
+// Matrix block (row r = 32*s + l, k-th stored column) lives at block slot  slice_ptr[s] + 32*k + l ;
+// its NB = n_eq*n_eq values are stored entry-major inside the (slice,k) group:
+//     val[(slice_ptr[s] + 32*k) * NB + e*32 + l]
+// so that a warp working on 32 consecutive rows reads/writes 256 contiguous bytes per entry.
+struct SellView {
+    int64_t n_rows;          // owned rows (nodes)
+    int64_t n_slices;
+    int64_t n_slots;         // total block slots incl. padding
+    const int32_t *slice_ptr;   // [n_slices+1] block-slot offsets
+    const int32_t *slice_width; // [n_slices]
+    const int32_t *col;         // [n_slots] column node (padding: the row itself)
+    // per-row cell fans (same slicing): entry (row, m) at inc_ptr[s] + 32*m + l
+    const int32_t *inc_ptr;     // [n_slices+1]
+    const int32_t *inc_width;   // [n_slices]
+    const int32_t *inc_vp;      // neighbour vertex shared with the previous cell of the fan
+    const int32_t *inc_vn;      // neighbour vertex shared with the next cell of the fan
+    const uint32_t *inc_pack;   // see PACK_* below
+    const uint32_t *row_pack;   // [n_slices*32]: n_inc | diag_slot<<8 | bc_value_index+1 <<16
+};
+
+// inc_pack bit layout
+#define PACK_SLOT_P(p) ((p)&0xffu)
+#define PACK_SLOT_N(p) (((p) >> 8) & 0xffu)
+#define PACK_MK_N(p) (((p) >> 16) & 0xfu)   // marker of exterior facet (a,p)  [opposite n]
+#define PACK_MK_P(p) (((p) >> 20) & 0xfu)   // marker of exterior facet (a,n)  [opposite p]
+#define PACK_FIRST(p) (((p) >> 24) & 1u)
+#define PACK_LAST(p) (((p) >> 25) & 1u)
+#define PACK_CLOSED(p) (((p) >> 26) & 1u)
+
+struct ModelParams {
+    int model_id;
+    int n_eq;
+    int n_fields;
+    int bc_comp;                 // component carrying Dirichlet conditions (-1: none)
+    double p[FEDMX_MAX_PARAMS];
+    double bc_values[FEDMX_MAX_BC];
+    double dt, dt_old, t;
+};
+
+struct HaloPlan {
+    int n_neighbors = 0;
+    std::vector<int> ranks;
+    std::vector<int> send_ptr, recv_ptr;
+    int32_t *d_send_nodes = nullptr, *d_recv_nodes = nullptr;
+    double *d_send_buf = nullptr, *d_recv_buf = nullptr;
+    int64_t n_send = 0, n_recv = 0;
+};
+
+struct fedmx_ctx {
+    int device = 0;
+    cudaStream_t stream = 0;
+    std::string err;
+    int64_t launches = 0;
+
+    // mesh / topology
+    int n_eq = 0;
+    int64_t n_vertices = 0;      // local vertices incl. ghosts
+    int64_t n_owned = 0;         // owned vertices are numbered first
+    double *d_coords = nullptr;  // [n_vertices][2]
+    SellView sell{};
+    std::vector<void *> owned_device;   // everything cudaMalloc'ed by set-up calls
+    // host copies for pattern export
+    std::vector<int32_t> h_rowptr, h_colidx;      // node-block CSR of the owned rows
+    std::vector<int32_t> h_slice_ptr;
+    // matrix values + block-Jacobi inverse
+    double *d_val = nullptr;     // [n_slots * NB]
+    double *d_dinv = nullptr;    // [n_slices*32 * NB] entry-major per slice
+    // model
+    ModelParams mp{};
+    const double *d_fields = nullptr;
+    // Dirichlet
+    std::vector<int32_t> bc_nodes, bc_value_index;
+    int bc_comp = -1;
+    // work vectors (sized n_eq * n_vertices)
+    double *d_res = nullptr, *d_dx = nullptr, *d_w = nullptr, *d_V = nullptr;
+    int krylov_restart_alloc = 0;
+    double *d_red = nullptr;     // reduction scratch
+    double *d_hess = nullptr;    // small device scalars for GMRES
+    double *h_pinned = nullptr;  // pinned host scratch
+    int64_t red_blocks = 0;
+    // comm
+    void *nccl_comm = nullptr;
+    int n_ranks = 1, rank = 0;
+    HaloPlan halo;
+};
+
+#define FEDMX_CHECK_CUDA(ctx, expr)                                                          \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(_e);                 \
+            return FEDMX_ECUDA;                                                              \
+        }                                                                                    \
+    } while (0)
+
+#define FEDMX_REQUIRE(ctx, cond, msg)                                                        \
+    do {                                                                                     \
+        if (!(cond)) {                                                                       \
+            (ctx)->err = std::string(msg);                                                   \
+            return FEDMX_EINVAL;                                                             \
+        }                                                                                    \
+    } while (0)
+
+template <class T>
+int fedmx_dev_alloc(fedmx_ctx *ctx, T **ptr, size_t count) {
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, (count ? count : 1) * sizeof(T));
+    if (e != cudaSuccess) {
+        ctx->err = std::string("cudaMalloc: ") + cudaGetErrorString(e);
+        return FEDMX_ENOMEM;
+    }
+    ctx->owned_device.push_back(p);
+    *ptr = (T *)p;
+    return FEDMX_OK;
+}
+
+template <class T>
+int fedmx_upload(fedmx_ctx *ctx, T **ptr, const std::vector<T> &h) {
+    int rc = fedmx_dev_alloc(ctx, ptr, h.size());
+    if (rc) return rc;
+    if (!h.empty()) FEDMX_CHECK_CUDA(ctx, cudaMemcpy(*ptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return FEDMX_OK;
+}
+
+// internal entry points shared between translation units
+int fedmx_ensure_workspace(fedmx_ctx *ctx, int restart);
+int fedmx_update_block_jacobi(fedmx_ctx *ctx);
+int fedmx_spmv_precond(fedmx_ctx *ctx, const double *d_x, double *d_y, bool precond);
+int fedmx_norm2_local(fedmx_ctx *ctx, const double *d_x, int64_t n, double *out, bool global);

@@ -1,0 +1,515 @@
+// FP64 sparse/dense vector kernels of the Newton-Krylov loop (sm_100a): SELL-32 block SpMV with the
+// block-Jacobi preconditioner fused into its epilogue, deterministic two-stage reductions (warp shuffles,
+// fixed summation order, no atomics), the fused multi-dot / multi-axpy of classical Gram-Schmidt, the
+// BDF2 error estimator, table interpolation and strided copies.
+//
+// Replaces PETSc MatMult / VecMDot / VecMAXPY / VecNorm / PCApply(bjacobi) under KSPGMRES
+// (reference call site: fedm/functions.py:1047 via linear_solver='gmres', fedm_streamer.py:32), numpy's
+// np.interp on dof vectors (fedm/functions.py:627-636, 739-747), df.norm (fedm/functions.py:1062-1064) and
+// FunctionAssigner.assign (fedm/functions.py:1050).  All of it is HBM-bandwidth-bound.
+#include <math.h>
+
+#include "fedmx_internal.h"
+
+namespace {
+
+constexpr int kRedThreads = 256;
+constexpr int kMaxRedBlocks = 1184;   // 148 SMs x 8
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Block-wide sum in a fixed order; result valid in thread 0.
+__device__ __forceinline__ double block_sum(double v, double *smem) {
+    v = warp_sum(v);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) smem[w] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (w == 0) {
+        r = (l < (blockDim.x >> 5)) ? smem[l] : 0.0;
+        r = warp_sum(r);
+    }
+    __syncthreads();
+    return r;
+}
+
+// ---- SpMV: y = A x  or  y = Dinv (A x), one thread per block row, SELL-32 entry-major storage ----------
+template <int NEQ, bool PRECOND>
+__global__ void __launch_bounds__(128) spmv_kernel(SellView S, const double *__restrict__ val,
+                                                   const double *__restrict__ dinv, const double *__restrict__ x,
+                                                   double *__restrict__ y) {
+    constexpr int NB = NEQ * NEQ;
+    const int64_t row = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t s = row / FEDMX_SLICE;
+    const int lane = int(row % FEDMX_SLICE);
+    if (s >= S.n_slices) return;
+    const int width = S.slice_width[s];
+    const int64_t gbase = S.slice_ptr[s];
+    double acc[NEQ];
+#pragma unroll
+    for (int k = 0; k < NEQ; ++k) acc[k] = 0.0;
+    for (int k = 0; k < width; ++k) {
+        const int64_t slot = gbase + int64_t(k) * FEDMX_SLICE;
+        const int32_t c = S.col[slot + lane];
+        const double *v = val + slot * NB + lane;
+        double xc[NEQ];
+#pragma unroll
+        for (int l = 0; l < NEQ; ++l) xc[l] = __ldg(x + int64_t(NEQ) * c + l);
+#pragma unroll
+        for (int i = 0; i < NEQ; ++i)
+#pragma unroll
+            for (int l = 0; l < NEQ; ++l) acc[i] = fma(__ldcs(v + (i * NEQ + l) * FEDMX_SLICE), xc[l], acc[i]);
+    }
+    if (row >= S.n_rows) return;
+    if (PRECOND) {
+        const double *d = dinv + s * FEDMX_SLICE * NB + lane;
+        double z[NEQ];
+#pragma unroll
+        for (int i = 0; i < NEQ; ++i) {
+            z[i] = 0.0;
+#pragma unroll
+            for (int l = 0; l < NEQ; ++l) z[i] = fma(d[(i * NEQ + l) * FEDMX_SLICE], acc[l], z[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < NEQ; ++i) y[int64_t(NEQ) * row + i] = z[i];
+    } else {
+#pragma unroll
+        for (int i = 0; i < NEQ; ++i) y[int64_t(NEQ) * row + i] = acc[i];
+    }
+}
+
+// ---- block-Jacobi: invert the diagonal blocks (Gauss-Jordan with partial pivoting in registers) ----------
+template <int NEQ>
+__global__ void block_jacobi_kernel(SellView S, const double *__restrict__ val, double *__restrict__ dinv) {
+    constexpr int NB = NEQ * NEQ;
+    const int64_t row = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t s = row / FEDMX_SLICE;
+    const int lane = int(row % FEDMX_SLICE);
+    if (s >= S.n_slices || row >= S.n_rows) return;
+    const int diag_slot = int((S.row_pack[row] >> 8) & 0xffu);
+    const double *v = val + (int64_t(S.slice_ptr[s]) + int64_t(diag_slot) * FEDMX_SLICE) * NB + lane;
+    double a[NEQ][NEQ], b[NEQ][NEQ];
+#pragma unroll
+    for (int i = 0; i < NEQ; ++i)
+#pragma unroll
+        for (int j = 0; j < NEQ; ++j) {
+            a[i][j] = v[(i * NEQ + j) * FEDMX_SLICE];
+            b[i][j] = (i == j) ? 1.0 : 0.0;
+        }
+#pragma unroll
+    for (int c = 0; c < NEQ; ++c) {
+        // partial pivoting without dynamic register indexing: swap rows pairwise
+#pragma unroll
+        for (int r = c + 1; r < NEQ; ++r) {
+            if (fabs(a[r][c]) > fabs(a[c][c])) {
+#pragma unroll
+                for (int j = 0; j < NEQ; ++j) {
+                    double t = a[c][j]; a[c][j] = a[r][j]; a[r][j] = t;
+                    t = b[c][j]; b[c][j] = b[r][j]; b[r][j] = t;
+                }
+            }
+        }
+        const double ip = 1.0 / a[c][c];
+#pragma unroll
+        for (int j = 0; j < NEQ; ++j) { a[c][j] *= ip; b[c][j] *= ip; }
+#pragma unroll
+        for (int r = 0; r < NEQ; ++r) {
+            if (r == c) continue;
+            const double f = a[r][c];
+#pragma unroll
+            for (int j = 0; j < NEQ; ++j) { a[r][j] -= f * a[c][j]; b[r][j] -= f * b[c][j]; }
+        }
+    }
+    double *d = dinv + s * FEDMX_SLICE * NB + lane;
+#pragma unroll
+    for (int i = 0; i < NEQ; ++i)
+#pragma unroll
+        for (int j = 0; j < NEQ; ++j) d[(i * NEQ + j) * FEDMX_SLICE] = b[i][j];
+}
+
+// z = Dinv r  (PCApply on a vector)
+template <int NEQ>
+__global__ void apply_dinv_kernel(SellView S, const double *__restrict__ dinv, const double *__restrict__ r,
+                                  double *__restrict__ z) {
+    constexpr int NB = NEQ * NEQ;
+    const int64_t row = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (row >= S.n_rows) return;
+    const int64_t s = row / FEDMX_SLICE;
+    const int lane = int(row % FEDMX_SLICE);
+    const double *d = dinv + s * FEDMX_SLICE * NB + lane;
+    double in[NEQ];
+#pragma unroll
+    for (int l = 0; l < NEQ; ++l) in[l] = r[int64_t(NEQ) * row + l];
+#pragma unroll
+    for (int i = 0; i < NEQ; ++i) {
+        double acc = 0.0;
+#pragma unroll
+        for (int l = 0; l < NEQ; ++l) acc = fma(d[(i * NEQ + l) * FEDMX_SLICE], in[l], acc);
+        z[int64_t(NEQ) * row + i] = acc;
+    }
+}
+
+// ---- reductions --------------------------------------------------------------------------------------------
+// partial[j*gridDim.x + blockIdx.x] = sum over this block's grid-stride chunk of V_j . w   (j < nvec)
+// and partial[nvec*gridDim.x + blockIdx.x] = w . w
+template <int JT>
+__global__ void __launch_bounds__(kRedThreads) multidot_kernel(const double *__restrict__ V, int64_t ld, int nvec,
+                                                               const double *__restrict__ w, int64_t n,
+                                                               double *__restrict__ partial, int with_ww) {
+    __shared__ double smem[32];
+    for (int j0 = 0; j0 < nvec || (j0 == 0 && with_ww); j0 += JT) {
+        double acc[JT], ww = 0.0;
+#pragma unroll
+        for (int j = 0; j < JT; ++j) acc[j] = 0.0;
+        for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+            const double wi = w[i];
+            if (j0 == 0) ww = fma(wi, wi, ww);
+#pragma unroll
+            for (int j = 0; j < JT; ++j)
+                if (j0 + j < nvec) acc[j] = fma(V[int64_t(j0 + j) * ld + i], wi, acc[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < JT; ++j) {
+            if (j0 + j < nvec) {
+                const double r = block_sum(acc[j], smem);
+                if (threadIdx.x == 0) partial[int64_t(j0 + j) * gridDim.x + blockIdx.x] = r;
+            }
+        }
+        if (j0 == 0 && with_ww) {
+            const double r = block_sum(ww, smem);
+            if (threadIdx.x == 0) partial[int64_t(nvec) * gridDim.x + blockIdx.x] = r;
+        }
+        if (nvec == 0) break;
+    }
+}
+
+// out[j] = sum_b partial[j*nblocks + b]  in fixed order; one block per j
+__global__ void __launch_bounds__(kRedThreads) finish_reduce_kernel(const double *__restrict__ partial, int nblocks,
+                                                                    double *__restrict__ out) {
+    __shared__ double smem[32];
+    const int j = blockIdx.x;
+    double acc = 0.0;
+    for (int b = threadIdx.x; b < nblocks; b += blockDim.x) acc += partial[int64_t(j) * nblocks + b];
+    const double r = block_sum(acc, smem);
+    if (threadIdx.x == 0) out[j] = r;
+}
+
+// w -= sum_j h[j] V_j ; partial[blockIdx] = ||w_new||^2 chunk
+__global__ void __launch_bounds__(kRedThreads) multiaxpy_norm_kernel(const double *__restrict__ V, int64_t ld, int nvec,
+                                                                     const double *__restrict__ h, double *__restrict__ w,
+                                                                     int64_t n, double *__restrict__ partial) {
+    __shared__ double smem[32];
+    __shared__ double hs[64];
+    if (threadIdx.x < nvec) hs[threadIdx.x] = h[threadIdx.x];
+    __syncthreads();
+    double ww = 0.0;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+        double wi = w[i];
+        for (int j = 0; j < nvec; ++j) wi = fma(-hs[j], V[int64_t(j) * ld + i], wi);
+        w[i] = wi;
+        ww = fma(wi, wi, ww);
+    }
+    const double r = block_sum(ww, smem);
+    if (threadIdx.x == 0) partial[blockIdx.x] = r;
+}
+
+// y = alpha * x  (alpha read from device memory as 1/ *inv_of if inv_of != null)
+__global__ void scale_copy_kernel(const double *__restrict__ x, double *__restrict__ y, int64_t n, double alpha,
+                                  const double *__restrict__ inv_of) {
+    const double a = inv_of ? alpha / *inv_of : alpha;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
+        y[i] = a * x[i];
+}
+
+// x += sum_j c[j] V_j
+__global__ void combine_kernel(const double *__restrict__ V, int64_t ld, int nvec, const double *__restrict__ c,
+                               double *__restrict__ x, int64_t n, double sign) {
+    __shared__ double cs[64];
+    if (threadIdx.x < nvec) cs[threadIdx.x] = c[threadIdx.x];
+    __syncthreads();
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+        double xi = x[i];
+        for (int j = 0; j < nvec; ++j) xi = fma(sign * cs[j], V[int64_t(j) * ld + i], xi);
+        x[i] = xi;
+    }
+}
+
+__global__ void axpy_kernel(double alpha, const double *__restrict__ x, double *__restrict__ y, int64_t n) {
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
+        y[i] = fma(alpha, x[i], y[i]);
+}
+
+// r = b - r   (r holds A x on entry)
+__global__ void residual_kernel(const double *__restrict__ b, double *__restrict__ r, int64_t n) {
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
+        r[i] = b[i] - r[i];
+}
+
+// error estimator partial sums: [0] = sum (a-b+eps)^2, [1] = sum (b+eps)^2 over component comp
+__global__ void __launch_bounds__(kRedThreads) error_norm_kernel(const double *__restrict__ a, const double *__restrict__ b,
+                                                                 int64_t n_nodes, int n_eq, int comp, double eps,
+                                                                 double *__restrict__ partial) {
+    __shared__ double smem[32];
+    double s0 = 0.0, s1 = 0.0;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n_nodes; i += int64_t(gridDim.x) * blockDim.x) {
+        const double bv = b[i * n_eq + comp];
+        const double d = a[i * n_eq + comp] - bv + eps;
+        const double e = bv + eps;
+        s0 = fma(d, d, s0);
+        s1 = fma(e, e, s1);
+    }
+    const double r0 = block_sum(s0, smem);
+    const double r1 = block_sum(s1, smem);
+    if (threadIdx.x == 0) {
+        partial[blockIdx.x] = r0;
+        partial[gridDim.x + blockIdx.x] = r1;
+    }
+}
+
+// np.interp: clamped piecewise-linear look-up, binary search per node
+__global__ void interp_kernel(const double *__restrict__ x, int64_t x_stride, int64_t n, const double *__restrict__ kx,
+                              const double *__restrict__ ky, int nt, double divisor, double *__restrict__ out,
+                              int64_t out_stride) {
+    extern __shared__ double tab[];
+    double *sx = tab, *sy = tab + nt;
+    for (int i = threadIdx.x; i < nt; i += blockDim.x) { sx[i] = kx[i]; sy[i] = ky[i]; }
+    __syncthreads();
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+        const double xv = x[i * x_stride];
+        double r;
+        if (xv != xv) r = xv;                      // NaN propagates, as in numpy
+        else if (xv <= sx[0]) r = sy[0];
+        else if (xv >= sx[nt - 1]) r = sy[nt - 1];
+        else {
+            int lo = 0, hi = nt - 1;               // invariant: sx[lo] <= xv < sx[hi]
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (sx[mid] <= xv) lo = mid; else hi = mid;
+            }
+            const double slope = (sy[lo + 1] - sy[lo]) / (sx[lo + 1] - sx[lo]);
+            // numpy's formula (compiled arr_interp); explicit rn ops so that nvcc does not contract it into an FMA
+            r = __dadd_rn(__dmul_rn(slope, xv - sx[lo]), sy[lo]);
+        }
+        out[i * out_stride] = r / divisor;
+    }
+}
+
+__global__ void strided_copy_kernel(const double *__restrict__ src, int64_t ss, int64_t so, double *__restrict__ dst,
+                                    int64_t ds, int64_t dof, int64_t n) {
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
+        dst[i * ds + dof] = src[i * ss + so];
+}
+
+inline unsigned grid_for(int64_t n, int threads, int cap = kMaxRedBlocks) {
+    int64_t b = (n + threads - 1) / threads;
+    if (b < 1) b = 1;
+    if (b > cap) b = cap;
+    return unsigned(b);
+}
+
+}  // namespace
+
+// ---- internal helpers used by the Krylov / Newton drivers ---------------------------------------------------
+int fedmx_ensure_workspace(fedmx_ctx *ctx, int restart) {
+    const int64_t n = int64_t(ctx->n_eq) * ctx->n_vertices;
+    int rc;
+    if (!ctx->d_res) {
+        if ((rc = fedmx_dev_alloc(ctx, &ctx->d_res, n))) return rc;
+        if ((rc = fedmx_dev_alloc(ctx, &ctx->d_dx, n))) return rc;
+        if ((rc = fedmx_dev_alloc(ctx, &ctx->d_w, n))) return rc;
+        if ((rc = fedmx_dev_alloc(ctx, &ctx->d_red, size_t(kMaxRedBlocks) * 72))) return rc;
+        if ((rc = fedmx_dev_alloc(ctx, &ctx->d_hess, 4096))) return rc;
+        FEDMX_CHECK_CUDA(ctx, cudaMemset(ctx->d_res, 0, n * sizeof(double)));
+        FEDMX_CHECK_CUDA(ctx, cudaMemset(ctx->d_dx, 0, n * sizeof(double)));
+        FEDMX_CHECK_CUDA(ctx, cudaMemset(ctx->d_w, 0, n * sizeof(double)));
+        FEDMX_CHECK_CUDA(ctx, cudaMallocHost((void **)&ctx->h_pinned, 4096 * sizeof(double)));
+    }
+    if (restart > ctx->krylov_restart_alloc) {
+        FEDMX_REQUIRE(ctx, restart <= 60, "GMRES restart > 60 unsupported");
+        // basis vectors are never freed individually; a larger restart allocates a new block
+        if ((rc = fedmx_dev_alloc(ctx, &ctx->d_V, size_t(restart + 1) * n))) return rc;
+        FEDMX_CHECK_CUDA(ctx, cudaMemset(ctx->d_V, 0, size_t(restart + 1) * n * sizeof(double)));
+        ctx->krylov_restart_alloc = restart;
+    }
+    return FEDMX_OK;
+}
+
+int fedmx_update_block_jacobi(fedmx_ctx *ctx) {
+    const int threads = 128;
+    const unsigned blocks = unsigned((ctx->sell.n_slices * FEDMX_SLICE + threads - 1) / threads);
+    switch (ctx->n_eq) {
+        case 1: block_jacobi_kernel<1><<<blocks, threads, 0, ctx->stream>>>(ctx->sell, ctx->d_val, ctx->d_dinv); break;
+        case 3: block_jacobi_kernel<3><<<blocks, threads, 0, ctx->stream>>>(ctx->sell, ctx->d_val, ctx->d_dinv); break;
+        case 5: block_jacobi_kernel<5><<<blocks, threads, 0, ctx->stream>>>(ctx->sell, ctx->d_val, ctx->d_dinv); break;
+        default: ctx->err = "block Jacobi: unsupported n_eq"; return FEDMX_EUNSUPPORTED;
+    }
+    ctx->launches++;
+    FEDMX_CHECK_CUDA(ctx, cudaGetLastError());
+    return FEDMX_OK;
+}
+
+int fedmx_spmv_precond(fedmx_ctx *ctx, const double *d_x, double *d_y, bool precond) {
+    const int threads = 128;
+    const unsigned blocks = unsigned((ctx->sell.n_slices * FEDMX_SLICE + threads - 1) / threads);
+#define SPMV_CASE(N)                                                                                              \
+    case N:                                                                                                       \
+        if (precond) spmv_kernel<N, true><<<blocks, threads, 0, ctx->stream>>>(ctx->sell, ctx->d_val, ctx->d_dinv, d_x, d_y); \
+        else spmv_kernel<N, false><<<blocks, threads, 0, ctx->stream>>>(ctx->sell, ctx->d_val, ctx->d_dinv, d_x, d_y);        \
+        break;
+    switch (ctx->n_eq) {
+        SPMV_CASE(1)
+        SPMV_CASE(3)
+        SPMV_CASE(5)
+        default: ctx->err = "spmv: unsupported n_eq"; return FEDMX_EUNSUPPORTED;
+    }
+#undef SPMV_CASE
+    ctx->launches++;
+    FEDMX_CHECK_CUDA(ctx, cudaGetLastError());
+    return FEDMX_OK;
+}
+
+int fedmx_apply_dinv(fedmx_ctx *ctx, const double *d_r, double *d_z) {
+    const int threads = 128;
+    const unsigned blocks = unsigned((ctx->n_owned + threads - 1) / threads);
+    switch (ctx->n_eq) {
+        case 1: apply_dinv_kernel<1><<<blocks, threads, 0, ctx->stream>>>(ctx->sell, ctx->d_dinv, d_r, d_z); break;
+        case 3: apply_dinv_kernel<3><<<blocks, threads, 0, ctx->stream>>>(ctx->sell, ctx->d_dinv, d_r, d_z); break;
+        case 5: apply_dinv_kernel<5><<<blocks, threads, 0, ctx->stream>>>(ctx->sell, ctx->d_dinv, d_r, d_z); break;
+        default: ctx->err = "apply_dinv: unsupported n_eq"; return FEDMX_EUNSUPPORTED;
+    }
+    ctx->launches++;
+    FEDMX_CHECK_CUDA(ctx, cudaGetLastError());
+    return FEDMX_OK;
+}
+
+// out_dev[0..nvec) = V_j . w (owned entries), out_dev[nvec] = w.w ; result stays on the device.
+int fedmx_multidot(fedmx_ctx *ctx, const double *V, int64_t ld, int nvec, const double *w, int64_t n, double *out_dev,
+                   bool with_ww) {
+    const unsigned blocks = grid_for(n, kRedThreads);
+    multidot_kernel<8><<<blocks, kRedThreads, 0, ctx->stream>>>(V, ld, nvec, w, n, ctx->d_red, with_ww ? 1 : 0);
+    finish_reduce_kernel<<<nvec + (with_ww ? 1 : 0), kRedThreads, 0, ctx->stream>>>(ctx->d_red, int(blocks), out_dev);
+    ctx->launches += 2;
+    FEDMX_CHECK_CUDA(ctx, cudaGetLastError());
+    return FEDMX_OK;
+}
+
+int fedmx_multiaxpy_norm(fedmx_ctx *ctx, const double *V, int64_t ld, int nvec, const double *h_dev, double *w, int64_t n,
+                         double *norm2_dev) {
+    const unsigned blocks = grid_for(n, kRedThreads);
+    multiaxpy_norm_kernel<<<blocks, kRedThreads, 0, ctx->stream>>>(V, ld, nvec, h_dev, w, n, ctx->d_red);
+    finish_reduce_kernel<<<1, kRedThreads, 0, ctx->stream>>>(ctx->d_red, int(blocks), norm2_dev);
+    ctx->launches += 2;
+    FEDMX_CHECK_CUDA(ctx, cudaGetLastError());
+    return FEDMX_OK;
+}
+
+int fedmx_scale_copy(fedmx_ctx *ctx, const double *x, double *y, int64_t n, double alpha, const double *inv_of_dev) {
+    scale_copy_kernel<<<grid_for(n, 256, 4736), 256, 0, ctx->stream>>>(x, y, n, alpha, inv_of_dev);
+    ctx->launches++;
+    FEDMX_CHECK_CUDA(ctx, cudaGetLastError());
+    return FEDMX_OK;
+}
+
+int fedmx_combine(fedmx_ctx *ctx, const double *V, int64_t ld, int nvec, const double *c_dev, double *x, int64_t n, double sign) {
+    combine_kernel<<<grid_for(n, 256, 4736), 256, 0, ctx->stream>>>(V, ld, nvec, c_dev, x, n, sign);
+    ctx->launches++;
+    FEDMX_CHECK_CUDA(ctx, cudaGetLastError());
+    return FEDMX_OK;
+}
+
+int fedmx_axpy(fedmx_ctx *ctx, double alpha, const double *x, double *y, int64_t n) {
+    axpy_kernel<<<grid_for(n, 256, 4736), 256, 0, ctx->stream>>>(alpha, x, y, n);
+    ctx->launches++;
+    FEDMX_CHECK_CUDA(ctx, cudaGetLastError());
+    return FEDMX_OK;
+}
+
+int fedmx_residual_from_ax(fedmx_ctx *ctx, const double *b, double *r, int64_t n) {
+    residual_kernel<<<grid_for(n, 256, 4736), 256, 0, ctx->stream>>>(b, r, n);
+    ctx->launches++;
+    FEDMX_CHECK_CUDA(ctx, cudaGetLastError());
+    return FEDMX_OK;
+}
+
+int fedmx_global_sum(fedmx_ctx *ctx, double *d_buf, int n);   // fedmx_comm.cu
+
+// sum of squares of the first n entries; global = allreduce over ranks. Synchronises the stream.
+int fedmx_norm2_local(fedmx_ctx *ctx, const double *d_x, int64_t n, double *out, bool global) {
+    int rc = fedmx_multidot(ctx, nullptr, 0, 0, d_x, n, ctx->d_hess + 2048, true);
+    if (rc) return rc;
+    if (global && ctx->n_ranks > 1 && (rc = fedmx_global_sum(ctx, ctx->d_hess + 2048, 1))) return rc;
+    FEDMX_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + 2048, ctx->d_hess + 2048, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    FEDMX_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = sqrt(ctx->h_pinned[2048]);
+    return FEDMX_OK;
+}
+
+// ---- C ABI --------------------------------------------------------------------------------------------------
+extern "C" int fedmx_spmv(fedmx_ctx *ctx, const double *d_x, double *d_y) {
+    if (!ctx) return FEDMX_EINVAL;
+    FEDMX_REQUIRE(ctx, ctx->d_val && d_x && d_y, "fedmx_spmv: no matrix / null vectors");
+    return fedmx_spmv_precond(ctx, d_x, d_y, false);
+}
+
+extern "C" int fedmx_norm2(fedmx_ctx *ctx, const double *d_x, int64_t n, double *out) {
+    if (!ctx) return FEDMX_EINVAL;
+    FEDMX_REQUIRE(ctx, ctx->d_red && d_x && out && n >= 0, "fedmx_norm2: bad arguments");
+    return fedmx_norm2_local(ctx, d_x, n, out, true);
+}
+
+extern "C" int fedmx_dot(fedmx_ctx *ctx, const double *d_x, const double *d_y, int64_t n, double *out) {
+    if (!ctx) return FEDMX_EINVAL;
+    FEDMX_REQUIRE(ctx, ctx->d_red && d_x && d_y && out && n >= 0, "fedmx_dot: bad arguments");
+    int rc = fedmx_multidot(ctx, d_x, n, 1, d_y, n, ctx->d_hess + 2048, false);
+    if (rc) return rc;
+    if (ctx->n_ranks > 1 && (rc = fedmx_global_sum(ctx, ctx->d_hess + 2048, 1))) return rc;
+    FEDMX_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + 2048, ctx->d_hess + 2048, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    FEDMX_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = ctx->h_pinned[2048];
+    return FEDMX_OK;
+}
+
+extern "C" int fedmx_error_norm(fedmx_ctx *ctx, const double *d_new, const double *d_old, int comp, double eps, double *err) {
+    if (!ctx) return FEDMX_EINVAL;
+    FEDMX_REQUIRE(ctx, ctx->d_red && d_new && d_old && err, "fedmx_error_norm: bad arguments");
+    FEDMX_REQUIRE(ctx, comp >= 0 && comp < ctx->n_eq, "fedmx_error_norm: bad component");
+    const unsigned blocks = grid_for(ctx->n_owned, kRedThreads);
+    error_norm_kernel<<<blocks, kRedThreads, 0, ctx->stream>>>(d_new, d_old, ctx->n_owned, ctx->n_eq, comp, eps, ctx->d_red);
+    finish_reduce_kernel<<<2, kRedThreads, 0, ctx->stream>>>(ctx->d_red, int(blocks), ctx->d_hess + 2048);
+    ctx->launches += 2;
+    FEDMX_CHECK_CUDA(ctx, cudaGetLastError());
+    int rc;
+    if (ctx->n_ranks > 1 && (rc = fedmx_global_sum(ctx, ctx->d_hess + 2048, 2))) return rc;
+    FEDMX_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + 2048, ctx->d_hess + 2048, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    FEDMX_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *err = sqrt(ctx->h_pinned[2048]) / sqrt(ctx->h_pinned[2049]);
+    return FEDMX_OK;
+}
+
+extern "C" int fedmx_interp_table(fedmx_ctx *ctx, const double *d_x, int64_t x_stride, int64_t n, const double *d_kx,
+                                  const double *d_ky, int n_table, double divisor, double *d_out, int64_t out_stride) {
+    if (!ctx) return FEDMX_EINVAL;
+    FEDMX_REQUIRE(ctx, d_x && d_kx && d_ky && d_out && n >= 0, "fedmx_interp_table: null argument");
+    FEDMX_REQUIRE(ctx, n_table >= 1 && n_table <= 2048, "fedmx_interp_table: table size must be in 1..2048");
+    if (n == 0) return FEDMX_OK;
+    interp_kernel<<<grid_for(n, 256, 4736), 256, 2 * n_table * sizeof(double), ctx->stream>>>(
+        d_x, x_stride, n, d_kx, d_ky, n_table, divisor, d_out, out_stride);
+    ctx->launches++;
+    FEDMX_CHECK_CUDA(ctx, cudaGetLastError());
+    return FEDMX_OK;
+}
+
+extern "C" int fedmx_strided_copy(fedmx_ctx *ctx, const double *d_src, int64_t src_stride, int64_t src_off, double *d_dst,
+                                  int64_t dst_stride, int64_t dst_off, int64_t n) {
+    if (!ctx) return FEDMX_EINVAL;
+    FEDMX_REQUIRE(ctx, d_src && d_dst && n >= 0, "fedmx_strided_copy: null argument");
+    if (n == 0) return FEDMX_OK;
+    strided_copy_kernel<<<grid_for(n, 256, 4736), 256, 0, ctx->stream>>>(d_src, src_stride, src_off, d_dst, dst_stride, dst_off, n);
+    ctx->launches++;
+    FEDMX_CHECK_CUDA(ctx, cudaGetLastError());
+    return FEDMX_OK;
+}

@@ -1,0 +1,182 @@
+// GMRES(restart) with left block-Jacobi preconditioning and the SNES-style Newton driver.
+//
+// Replaces PETSc KSPGMRES (classical Gram-Schmidt, restart 30, convergence on the preconditioned residual,
+// zero initial guess) + PCBJACOBI and SNES newtonls with the basic (full-step) line search behind
+// `nonlinear_solver.solve(problem, u_new.vector())` (reference: fedm/functions.py:1047; solver parameters
+// fedm_streamer.py:302-305).  Everything that touches a vector runs on the device; the host only keeps the
+// (restart+1) x restart Hessenberg matrix and reads one small pinned buffer per Krylov iteration.
+#include <math.h>
+
+#include <vector>
+
+#include "fedmx_internal.h"
+
+int fedmx_apply_dinv(fedmx_ctx *ctx, const double *d_r, double *d_z);
+int fedmx_multidot(fedmx_ctx *ctx, const double *V, int64_t ld, int nvec, const double *w, int64_t n, double *out_dev, bool with_ww);
+int fedmx_multiaxpy_norm(fedmx_ctx *ctx, const double *V, int64_t ld, int nvec, const double *h_dev, double *w, int64_t n, double *norm2_dev);
+int fedmx_scale_copy(fedmx_ctx *ctx, const double *x, double *y, int64_t n, double alpha, const double *inv_of_dev);
+int fedmx_combine(fedmx_ctx *ctx, const double *V, int64_t ld, int nvec, const double *c_dev, double *x, int64_t n, double sign);
+int fedmx_axpy(fedmx_ctx *ctx, double alpha, const double *x, double *y, int64_t n);
+int fedmx_residual_from_ax(fedmx_ctx *ctx, const double *b, double *r, int64_t n);
+int fedmx_global_sum(fedmx_ctx *ctx, double *d_buf, int n);
+int fedmx_halo_exchange_internal(fedmx_ctx *ctx, double *d_vec, int n_comp);
+int fedmx_assemble_internal(fedmx_ctx *ctx, const double *d_x, double dt, double dt_old, double t,
+                            const double *h_bc_values, int n_bc_values, double *d_b, bool jac);
+
+namespace {
+
+// d_hess layout (doubles): [0..64) h column / y coefficients, [64] norm^2 scratch
+int gmres_impl(fedmx_ctx *ctx, const double *d_b, double *d_x, int restart, double rtol, double atol, int max_it,
+               int *iters, double *rnorm_out, int *converged) {
+    int rc;
+    if ((rc = fedmx_ensure_workspace(ctx, restart))) return rc;
+    const int64_t ld = int64_t(ctx->n_eq) * ctx->n_vertices;     // vector length incl. ghosts
+    const int64_t n = int64_t(ctx->n_eq) * ctx->n_owned;         // owned entries
+    double *V = ctx->d_V, *w = ctx->d_w;
+    double *dh = ctx->d_hess, *hp = ctx->h_pinned;
+    const bool multi = ctx->n_ranks > 1;
+    std::vector<double> H(size_t(restart + 1) * restart, 0.0), cs(restart), sn(restart), g(restart + 1);
+    auto Hm = [&](int i, int j) -> double & { return H[size_t(i) * restart + j]; };
+
+    FEDMX_CHECK_CUDA(ctx, cudaMemsetAsync(d_x, 0, ld * sizeof(double), ctx->stream));
+    // r0 = Dinv b  (x0 = 0)
+    if ((rc = fedmx_apply_dinv(ctx, d_b, w))) return rc;
+    double beta;
+    if ((rc = fedmx_norm2_local(ctx, w, n, &beta, true))) return rc;
+    const double tol = fmax(rtol * beta, atol);
+    *iters = 0;
+    *converged = 0;
+    *rnorm_out = beta;
+    if (!(beta == beta) || isinf(beta)) return FEDMX_OK;        // NaN/Inf: not converged
+    if (beta <= tol || beta == 0.0) { *converged = 1; return FEDMX_OK; }
+    int its = 0;
+    double rnorm = beta;
+    while (its < max_it) {
+        // V0 = r / beta  (w holds the preconditioned residual)
+        if ((rc = fedmx_scale_copy(ctx, w, V, n, 1.0 / beta, nullptr))) return rc;
+        for (int i = 0; i <= restart; ++i) g[i] = 0.0;
+        g[0] = beta;
+        int k_used = 0;
+        bool done = false;
+        for (int k = 0; k < restart && its < max_it; ++k) {
+            double *Vk = V + int64_t(k) * ld;
+            if (multi && (rc = fedmx_halo_exchange_internal(ctx, Vk, ctx->n_eq))) return rc;
+            if ((rc = fedmx_spmv_precond(ctx, Vk, w, true))) return rc;
+            if ((rc = fedmx_multidot(ctx, V, ld, k + 1, w, n, dh, false))) return rc;
+            if (multi && (rc = fedmx_global_sum(ctx, dh, k + 1))) return rc;
+            if ((rc = fedmx_multiaxpy_norm(ctx, V, ld, k + 1, dh, w, n, dh + 64))) return rc;
+            if (multi && (rc = fedmx_global_sum(ctx, dh + 64, 1))) return rc;
+            // next basis vector: V_{k+1} = w / ||w||   (norm read on the device)
+            if (k + 1 <= restart) {
+                if ((rc = fedmx_scale_copy(ctx, w, V + int64_t(k + 1) * ld, n, 1.0, nullptr))) return rc;
+            }
+            FEDMX_CHECK_CUDA(ctx, cudaMemcpyAsync(hp, dh, 65 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            FEDMX_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            const double hk1 = sqrt(hp[64]);
+            for (int i = 0; i <= k; ++i) Hm(i, k) = hp[i];
+            Hm(k + 1, k) = hk1;
+            if (hk1 > 0.0) {
+                // normalise in place (scale_copy above stored the unnormalised vector)
+                if ((rc = fedmx_scale_copy(ctx, V + int64_t(k + 1) * ld, V + int64_t(k + 1) * ld, n, 1.0 / hk1, nullptr))) return rc;
+            }
+            for (int i = 0; i < k; ++i) {
+                const double t = cs[i] * Hm(i, k) + sn[i] * Hm(i + 1, k);
+                Hm(i + 1, k) = -sn[i] * Hm(i, k) + cs[i] * Hm(i + 1, k);
+                Hm(i, k) = t;
+            }
+            const double d = hypot(Hm(k, k), Hm(k + 1, k));
+            if (d == 0.0 || !(d == d)) { *iters = its; *rnorm_out = rnorm; return FEDMX_OK; }
+            cs[k] = Hm(k, k) / d;
+            sn[k] = Hm(k + 1, k) / d;
+            Hm(k, k) = d;
+            Hm(k + 1, k) = 0.0;
+            g[k + 1] = -sn[k] * g[k];
+            g[k] = cs[k] * g[k];
+            rnorm = fabs(g[k + 1]);
+            ++its;
+            k_used = k + 1;
+            if (!(rnorm == rnorm)) { *iters = its; *rnorm_out = rnorm; return FEDMX_OK; }
+            if (rnorm <= tol) { done = true; break; }
+        }
+        // back substitution on the host, x += V y on the device
+        std::vector<double> y(k_used, 0.0);
+        for (int i = k_used - 1; i >= 0; --i) {
+            double s = g[i];
+            for (int j = i + 1; j < k_used; ++j) s -= Hm(i, j) * y[j];
+            y[i] = s / Hm(i, i);
+        }
+        for (int i = 0; i < k_used; ++i) hp[128 + i] = y[i];
+        FEDMX_CHECK_CUDA(ctx, cudaMemcpyAsync(dh + 128, hp + 128, k_used * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        if ((rc = fedmx_combine(ctx, V, ld, k_used, dh + 128, d_x, n, 1.0))) return rc;
+        if (done) { *converged = 1; break; }
+        if (its >= max_it) break;
+        // restart: r = Dinv (b - A x)
+        if (multi && (rc = fedmx_halo_exchange_internal(ctx, d_x, ctx->n_eq))) return rc;
+        if ((rc = fedmx_spmv_precond(ctx, d_x, w, false))) return rc;
+        if ((rc = fedmx_residual_from_ax(ctx, d_b, w, n))) return rc;
+        if ((rc = fedmx_apply_dinv(ctx, w, w))) return rc;
+        if ((rc = fedmx_norm2_local(ctx, w, n, &beta, true))) return rc;
+        rnorm = beta;
+        if (beta <= tol) { *converged = 1; break; }
+    }
+    *iters = its;
+    *rnorm_out = rnorm;
+    return FEDMX_OK;
+}
+
+}  // namespace
+
+extern "C" int fedmx_gmres(fedmx_ctx *ctx, const double *d_b, double *d_x, int restart, double rtol, double atol,
+                           int max_it, int *iters, double *rnorm, int *converged) {
+    if (!ctx) return FEDMX_EINVAL;
+    FEDMX_REQUIRE(ctx, ctx->d_val && d_b && d_x && iters && rnorm && converged, "fedmx_gmres: bad arguments");
+    FEDMX_REQUIRE(ctx, restart >= 1 && restart <= 60, "fedmx_gmres: restart must be in 1..60");
+    return gmres_impl(ctx, d_b, d_x, restart, rtol, atol, max_it, iters, rnorm, converged);
+}
+
+extern "C" int fedmx_newton_solve(fedmx_ctx *ctx, double *d_x, double dt, double dt_old, double t,
+                                  const double *h_bc_values, int n_bc_values, const fedmx_newton_params *prm,
+                                  fedmx_newton_result *res) {
+    if (!ctx) return FEDMX_EINVAL;
+    FEDMX_REQUIRE(ctx, d_x && prm && res, "fedmx_newton_solve: null argument");
+    FEDMX_REQUIRE(ctx, prm->ksp_restart >= 1 && prm->ksp_restart <= 60, "fedmx_newton_solve: bad ksp_restart");
+    int rc;
+    if ((rc = fedmx_ensure_workspace(ctx, prm->ksp_restart))) return rc;
+    const int64_t n = int64_t(ctx->n_eq) * ctx->n_owned;
+    const bool multi = ctx->n_ranks > 1;
+    *res = fedmx_newton_result{};
+    if (multi && (rc = fedmx_halo_exchange_internal(ctx, d_x, ctx->n_eq))) return rc;
+    if ((rc = fedmx_assemble_internal(ctx, d_x, dt, dt_old, t, h_bc_values, n_bc_values, ctx->d_res, false))) return rc;
+    double fnorm;
+    if ((rc = fedmx_norm2_local(ctx, ctx->d_res, n, &fnorm, true))) return rc;
+    res->fnorm0 = res->fnorm = fnorm;
+    res->fnorm_history[0] = fnorm;
+    if (!(fnorm == fnorm) || isinf(fnorm)) { res->reason = FEDMX_SNES_DIVERGED_FNORM_NAN; return FEDMX_OK; }
+    if (fnorm < prm->atol) { res->reason = FEDMX_SNES_CONVERGED_FNORM_ABS; return FEDMX_OK; }
+    for (int it = 1; it <= prm->max_it; ++it) {
+        if ((rc = fedmx_assemble_internal(ctx, d_x, dt, dt_old, t, h_bc_values, n_bc_values, nullptr, true))) return rc;
+        if ((rc = fedmx_update_block_jacobi(ctx))) return rc;
+        int kits = 0, kconv = 0;
+        double krn = 0.0;
+        if ((rc = gmres_impl(ctx, ctx->d_res, ctx->d_dx, prm->ksp_restart, prm->ksp_rtol, prm->ksp_atol, prm->ksp_max_it,
+                             &kits, &krn, &kconv))) return rc;
+        res->linear_iterations += kits;
+        res->iterations = it;
+        if (!kconv) { res->reason = FEDMX_SNES_DIVERGED_LINEAR_SOLVE; return FEDMX_OK; }
+        if ((rc = fedmx_axpy(ctx, -1.0, ctx->d_dx, d_x, n))) return rc;      // x <- x - delta (full step)
+        if (multi && (rc = fedmx_halo_exchange_internal(ctx, d_x, ctx->n_eq))) return rc;
+        if ((rc = fedmx_assemble_internal(ctx, d_x, dt, dt_old, t, h_bc_values, n_bc_values, ctx->d_res, false))) return rc;
+        if ((rc = fedmx_norm2_local(ctx, ctx->d_res, n, &fnorm, true))) return rc;
+        res->fnorm = fnorm;
+        if (it < 64) res->fnorm_history[it] = fnorm;
+        if (!(fnorm == fnorm) || isinf(fnorm)) { res->reason = FEDMX_SNES_DIVERGED_FNORM_NAN; return FEDMX_OK; }
+        if (fnorm < prm->atol) { res->reason = FEDMX_SNES_CONVERGED_FNORM_ABS; return FEDMX_OK; }
+        if (fnorm <= prm->rtol * res->fnorm0) { res->reason = FEDMX_SNES_CONVERGED_FNORM_RELATIVE; return FEDMX_OK; }
+        double dxn, xn;
+        if ((rc = fedmx_norm2_local(ctx, ctx->d_dx, n, &dxn, true))) return rc;
+        if ((rc = fedmx_norm2_local(ctx, d_x, n, &xn, true))) return rc;
+        if (dxn < prm->stol * xn) { res->reason = FEDMX_SNES_CONVERGED_SNORM_RELATIVE; return FEDMX_OK; }
+    }
+    res->reason = FEDMX_SNES_DIVERGED_MAX_IT;
+    return FEDMX_OK;
+}

@@ -1,0 +1,191 @@
+"""Device-resident nonlinear problem: the Python face of libfedmx (ctypes; torch tensors as buffers only).
+
+Plays the role of dolfin's ``NonlinearProblem`` + ``PETScSNESSolver`` pair for the FEDM form family:
+``HotPath.residual`` / ``HotPath.jacobian`` are ``Problem.F`` / ``Problem.J`` (fedm/functions.py:188-202),
+``HotPath.newton`` is ``nonlinear_solver.solve(problem, x)`` (fedm/functions.py:1047) including its
+"raise on non-convergence" behaviour, ``HotPath.error_norm`` the estimator of fedm/functions.py:1062-1064.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import lib as _l
+
+MODEL_STREAMER, MODEL_TOF, MODEL_GLOW, MODEL_POISSON = 1, 2, 3, 4
+
+SNES_REASONS = {2: "CONVERGED_FNORM_ABS", 3: "CONVERGED_FNORM_RELATIVE", 4: "CONVERGED_SNORM_RELATIVE",
+                -3: "DIVERGED_LINEAR_SOLVE", -4: "DIVERGED_FNORM_NAN", -5: "DIVERGED_MAX_IT"}
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    if isinstance(t, torch.Tensor):
+        if not t.is_cuda or t.dtype != torch.float64 or not t.is_contiguous():
+            raise ValueError("expected a contiguous float64 CUDA tensor")
+        return C.c_void_p(t.data_ptr())
+    raise TypeError(type(t))
+
+
+def _np_ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class HotPath:
+    def __init__(self, device=0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("fedm_b200.HotPath needs a CUDA device (there is no CPU fallback)")
+        self.lib = _l.load()
+        self.device = torch.device("cuda", device)
+        torch.cuda.set_device(self.device)
+        h = C.c_void_p()
+        rc = self.lib.fedmx_ctx_create(device, C.byref(h))
+        if rc != 0:
+            raise _l.FedmxError(f"fedmx_ctx_create failed ({rc})")
+        self.h = h
+        self.n_eq = 0
+        self.n_vertices = self.n_owned = 0
+        self.bc_values = np.zeros(0)
+        self.fields = None
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.fedmx_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise _l.FedmxError(f"libfedmx error {rc}: {self.lib.fedmx_last_error(self.h).decode()}")
+
+    # ---- set-up -------------------------------------------------------------------------------------
+    def set_mesh(self, n_eq, coords, cells, facet_vertices=None, facet_markers=None, n_owned=None):
+        coords = np.ascontiguousarray(coords, dtype=np.float64)
+        cells = np.ascontiguousarray(cells, dtype=np.int32)
+        nf = 0 if facet_vertices is None else len(facet_vertices)
+        fv = np.ascontiguousarray(facet_vertices if nf else np.zeros((0, 2)), dtype=np.int32)
+        fm = np.ascontiguousarray(facet_markers if nf else np.zeros(0), dtype=np.int32)
+        n_owned = coords.shape[0] if n_owned is None else int(n_owned)
+        self._ck(self.lib.fedmx_mesh_set(self.h, n_eq, coords.shape[0], _np_ptr(coords), cells.shape[0], _np_ptr(cells),
+                                         nf, _np_ptr(fv), _np_ptr(fm), n_owned))
+        self.n_eq, self.n_vertices, self.n_owned = n_eq, coords.shape[0], n_owned
+
+    def set_dirichlet(self, comp, nodes, value_index):
+        nodes = np.ascontiguousarray(nodes, dtype=np.int32)
+        vi = np.ascontiguousarray(value_index, dtype=np.int32)
+        self._ck(self.lib.fedmx_dirichlet_set(self.h, comp, nodes.size, _np_ptr(nodes), _np_ptr(vi)))
+
+    def set_model(self, model_id, params, n_fields):
+        p = np.ascontiguousarray(params, dtype=np.float64)
+        self._ck(self.lib.fedmx_model_set(self.h, model_id, p.size, _np_ptr(p)))
+        self.fields = torch.zeros((self.n_vertices, max(n_fields, 1)), dtype=torch.float64, device=self.device)
+        self.n_fields = n_fields
+        self._ck(self.lib.fedmx_fields_bind(self.h, n_fields, _ptr(self.fields)))
+
+    def pattern(self):
+        nr, nz = C.c_int64(), C.c_int64()
+        self._ck(self.lib.fedmx_pattern_get(self.h, C.byref(nr), C.byref(nz), None, None))
+        rowptr = np.empty(nr.value + 1, dtype=np.int32)
+        colidx = np.empty(nz.value, dtype=np.int32)
+        self._ck(self.lib.fedmx_pattern_get(self.h, C.byref(nr), C.byref(nz), _np_ptr(rowptr), _np_ptr(colidx)))
+        return rowptr, colidx
+
+    def matrix_bsr(self):
+        rowptr, colidx = self.pattern()
+        vals = np.empty((colidx.size, self.n_eq, self.n_eq))
+        self._ck(self.lib.fedmx_matrix_get_bsr(self.h, _np_ptr(vals)))
+        return rowptr, colidx, vals
+
+    def new_vector(self):
+        return torch.zeros(self.n_vertices * self.n_eq, dtype=torch.float64, device=self.device)
+
+    # ---- per-step calls ------------------------------------------------------------------------------
+    def _bc(self):
+        b = np.ascontiguousarray(self.bc_values, dtype=np.float64)
+        self._keep = [b]
+        return _np_ptr(b) if b.size else None, int(b.size)
+
+    def bdf2_history(self, n_hist, x_old, x_old1, dt, dt_old, field_offset=0):
+        self._ck(self.lib.fedmx_bdf2_history(self.h, n_hist, _ptr(x_old), _ptr(x_old1), dt, dt_old, _ptr(self.fields),
+                                             self.fields.shape[1], field_offset))
+
+    def residual(self, x, dt, dt_old, t=0.0, out=None):
+        out = self.new_vector() if out is None else out
+        p, n = self._bc()
+        self._ck(self.lib.fedmx_assemble_residual(self.h, _ptr(x), dt, dt_old, t, p, n, _ptr(out)))
+        return out
+
+    def jacobian(self, x, dt, dt_old, t=0.0, residual_out=None):
+        p, n = self._bc()
+        self._ck(self.lib.fedmx_assemble_jacobian(self.h, _ptr(x), dt, dt_old, t, p, n, _ptr(residual_out)))
+
+    def spmv(self, x, y=None):
+        y = self.new_vector() if y is None else y
+        self._ck(self.lib.fedmx_spmv(self.h, _ptr(x), _ptr(y)))
+        return y
+
+    def norm2(self, x, n=None):
+        out = C.c_double()
+        self._ck(self.lib.fedmx_norm2(self.h, _ptr(x), self.n_owned * self.n_eq if n is None else n, C.byref(out)))
+        return out.value
+
+    def gmres(self, b, x=None, restart=30, rtol=1e-5, atol=1e-50, max_it=10000):
+        x = self.new_vector() if x is None else x
+        its, conv, rn = C.c_int(), C.c_int(), C.c_double()
+        self._ck(self.lib.fedmx_gmres(self.h, _ptr(b), _ptr(x), restart, rtol, atol, max_it, C.byref(its), C.byref(rn),
+                                      C.byref(conv)))
+        return x, its.value, bool(conv.value), rn.value
+
+    def newton(self, x, dt, dt_old, t=0.0, rtol=1e-9, atol=1e-10, stol=1e-16, max_it=50, ksp_restart=30,
+               ksp_rtol=1e-5, ksp_atol=1e-50, ksp_max_it=10000, raise_on_failure=True):
+        """x is updated in place.  Returns the NewtonResult; raises RuntimeError on divergence like dolfin's
+        PETScSNESSolver with error_on_nonconvergence=True (that is what fedm's adaptive_solver catches)."""
+        prm = _l.NewtonParams(rtol, atol, stol, max_it, ksp_restart, ksp_rtol, ksp_atol, ksp_max_it)
+        res = _l.NewtonResult()
+        p, n = self._bc()
+        self._ck(self.lib.fedmx_newton_solve(self.h, _ptr(x), dt, dt_old, t, p, n, C.byref(prm), C.byref(res)))
+        if res.reason < 0 and raise_on_failure:
+            raise RuntimeError(f"Newton solver did not converge: {SNES_REASONS.get(res.reason, res.reason)} after "
+                               f"{res.iterations} iterations (|F| = {res.fnorm:g})")
+        return res
+
+    def error_norm(self, x_new, x_old, comp, eps=3.0e-16):
+        out = C.c_double()
+        self._ck(self.lib.fedmx_error_norm(self.h, _ptr(x_new), _ptr(x_old), comp, eps, C.byref(out)))
+        return out.value
+
+    def interp_table(self, x, kx, ky, out, divisor=1.0, x_stride=1, out_stride=1, n=None):
+        n = (x.numel() // x_stride) if n is None else n
+        self._ck(self.lib.fedmx_interp_table(self.h, _ptr(x), x_stride, n, _ptr(kx), _ptr(ky), kx.numel(), divisor,
+                                             _ptr(out), out_stride))
+        return out
+
+    def strided_copy(self, src, src_stride, src_off, dst, dst_stride, dst_off, n):
+        self._ck(self.lib.fedmx_strided_copy(self.h, _ptr(src), src_stride, src_off, _ptr(dst), dst_stride, dst_off, n))
+
+    def launch_count(self, reset=False):
+        return int(self.lib.fedmx_launch_count(self.h, 1 if reset else 0))
+
+    # ---- multi-GPU ------------------------------------------------------------------------------------
+    def comm_init(self, n_ranks, rank, unique_id):
+        self._ck(self.lib.fedmx_comm_init(self.h, n_ranks, rank, unique_id))
+
+    def set_halo(self, neighbor_ranks, send_ptr, send_nodes, recv_ptr, recv_nodes):
+        a = [np.ascontiguousarray(v, dtype=np.int32) for v in (neighbor_ranks, send_ptr, send_nodes, recv_ptr, recv_nodes)]
+        self._ck(self.lib.fedmx_halo_set(self.h, a[0].size, *[_np_ptr(v) for v in a]))
+
+    def halo_exchange(self, vec, n_comp=None):
+        self._ck(self.lib.fedmx_halo_exchange(self.h, _ptr(vec), self.n_eq if n_comp is None else n_comp))
+
+
+def pid_step(dt, err, tol, dt_min, dt_max):
+    """``adaptive_timestep`` (fedm/functions.py:915-927) through the library's host libm implementation."""
+    e = (C.c_double * 3)(*[float(v) for v in err])
+    return float(_l.load().fedmx_pid_step(dt, e, tol, dt_min, dt_max))

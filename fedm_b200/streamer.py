@@ -1,0 +1,134 @@
+"""Positive-streamer benchmark case on the device path.
+
+Host-side mirror of tests/integrated_tests/streamer_discharge/fedm_streamer.py (reference): same constants
+(:39-46), boundaries (:102-114), initial condition (:177-180), initial Poisson solve (:194-223), coefficient
+strings (e_Nb.dat / e_ND.dat / :247), Dirichlet conditions (:241), SNES parameters (:302-305) and time loop
+(:312-353).  The reference's mesh.xml is not available, so the mesh is a dolfin-style structured grid
+(optionally graded towards the axis).  All per-step arithmetic runs in libfedmx on the GPU.
+"""
+import numpy as np
+import torch
+
+from . import hotpath as hp
+from .mesh import rectangle
+from .timestepping import adaptive_timestep, attempt_until_accepted
+
+ELEMENTARY_CHARGE = 1.6021766208e-19
+EPSILON_0 = 8.854187817e-12
+BOX = 0.0125
+U_W = 18750.0
+BOUNDARIES = [["line", 0.0, 0.0, 0.0, BOX], ["line", BOX, BOX, 0.0, BOX],
+              ["line", 0.0, BOX, 0.0, 0.0], ["line", 0.0, BOX, BOX, BOX]]
+# mobility 2.3987*E_m**(-0.26), diffusion 4.3628e-3*E_m**0.22, alpha = (1.1944e6 + 4.3666e26*E_m**(-3))*exp(-2.73e7/E_m) - 340.75
+STREAMER_PARAMS = [2.3987, -0.26, 4.3628e-3, 0.22, 1.1944e6, 4.3666e26, 2.73e7, 340.75,
+                   ELEMENTARY_CHARGE / EPSILON_0, float((1 << 1) | (1 << 2))]
+
+
+def streamer_mesh(n, grading_power=1.0):
+    if grading_power == 1.0:
+        return rectangle((0.0, 0.0), (BOX, BOX), n, n, "right")
+    return rectangle((0.0, 0.0), (BOX, BOX), n, n, "right", map_x=lambda s: s ** grading_power)
+
+
+class StreamerCase:
+    n_eq = 3
+
+    def __init__(self, n=64, grading_power=1.0, device=0, mesh=None, newton_rtol=1e-4, newton_max_it=20,
+                 ksp_rtol=1e-5, ksp_restart=30, ksp_max_it=10000):
+        self.mesh = mesh if mesh is not None else streamer_mesh(n, grading_power)
+        m = self.mesh
+        self.hot = hp.HotPath(device)
+        fv = m.exterior_facets()
+        self.hot.set_mesh(3, m.coords, m.cells, fv, m.mark_lines(BOUNDARIES))
+        z = m.coords[:, 1]
+        cath = np.nonzero(np.abs(z) < 3e-16)[0]
+        anod = np.nonzero(np.abs(z - BOX) < 3e-16)[0]
+        self.bc_nodes = np.concatenate([cath, anod]).astype(np.int32)
+        self.bc_index = np.concatenate([np.zeros(cath.size), np.ones(anod.size)]).astype(np.int32)
+        self.hot.set_dirichlet(2, self.bc_nodes, self.bc_index)
+        self.hot.bc_values = np.array([0.0, U_W])
+        self.hot.set_model(hp.MODEL_STREAMER, STREAMER_PARAMS, 2)
+        self.newton_kw = dict(rtol=newton_rtol, max_it=newton_max_it, ksp_rtol=ksp_rtol, ksp_restart=ksp_restart,
+                              ksp_max_it=ksp_max_it)
+        dev = self.hot.device
+        self.x_new = self.hot.new_vector()
+        self.x_old = self.hot.new_vector()
+        self.x_old1 = self.hot.new_vector()
+        self.t = 0.0
+        self.dt, self.dt_old = 5e-12, 1e30
+        self.dt_min, self.dt_max, self.ttol = 1e-15, 5e-12, 1e-3
+        self.max_error = [1, 1, 1]
+        self.rows = []
+        self.stats = []
+        self.device = dev
+
+    # ---- initial condition + initial Poisson solve ---------------------------------------------------
+    def initial_log_densities(self):
+        r, z = self.mesh.coords[:, 0], self.mesh.coords[:, 1]
+        ui = np.log(1e13 + 5e18 * np.exp(-(r ** 2 + (z - 1e-2) ** 2) / (0.4e-3) ** 2))
+        ue = np.full_like(ui, np.log(1e13))
+        return ui, ue
+
+    def solve_initial_potential(self, ui, ue, ksp_rtol=1e-13):
+        m = self.mesh
+        pot = hp.HotPath(self.device.index or 0)
+        pot.set_mesh(1, m.coords, m.cells)
+        pot.set_dirichlet(0, self.bc_nodes, self.bc_index)
+        pot.bc_values = np.array([0.0, U_W])
+        pot.set_model(hp.MODEL_POISSON, [ELEMENTARY_CHARGE / EPSILON_0], 2)
+        pot.fields.copy_(torch.from_numpy(np.stack([ui, ue], axis=1)))
+        phi = pot.new_vector()
+        res = pot.newton(phi, 1.0, 1.0, rtol=1e-12, atol=0.0, max_it=5, ksp_rtol=ksp_rtol, ksp_restart=60,
+                         ksp_max_it=200000)
+        self.initial_poisson_stats = (res.iterations, res.linear_iterations, res.fnorm0, res.fnorm)
+        out = phi.cpu().numpy()
+        pot.close()
+        return out
+
+    def set_initial_state(self, x0=None):
+        if x0 is None:
+            ui, ue = self.initial_log_densities()
+            phi = self.solve_initial_potential(ui, ue)
+            x0 = np.stack([ui, ue, phi], axis=1).ravel()
+        x0 = torch.from_numpy(np.ascontiguousarray(x0)).to(self.device)
+        self.x_new.copy_(x0)
+        self.x_old.copy_(x0)
+        self.x_old1.zero_()
+        self.t = 0.0
+        self.dt, self.dt_old = 5e-12, 1e30
+        self.max_error = [1, 1, 1]
+        self.rows = []
+        self.stats = []
+
+    # ---- one accepted step (fedm_streamer.py:313-348) -------------------------------------------------
+    def step(self):
+        hot = self.hot
+        self.x_old1.copy_(self.x_old)
+        self.x_old.copy_(self.x_new)
+
+        def solve_attempt(t_new, dt):
+            hot.bdf2_history(2, self.x_old, self.x_old1, dt, self.dt_old)
+            res = hot.newton(self.x_new, dt, self.dt_old, t_new, **self.newton_kw)
+            self.stats.append((res.iterations, res.linear_iterations, res.fnorm0, res.fnorm))
+            return hot.error_norm(self.x_new, self.x_old, 1)       # LFA: variable index -2 = ln n_e
+
+        def reset():
+            self.x_new.copy_(self.x_old)
+
+        self.t, self.dt, attempts = attempt_until_accepted(
+            solve_attempt, reset, self.t, self.dt, self.dt_old, self.ttol, self.dt_min, self.max_error,
+            error_log=lambda row: self.rows.append(tuple(float(v) for v in row.split())))
+        self.dt_old = self.dt
+        self.dt = adaptive_timestep(self.dt, self.max_error, self.ttol, self.dt_min, self.dt_max)
+        self.max_error[2] = self.max_error[1]
+        self.max_error[1] = self.max_error[0]
+        return attempts
+
+    def run(self, T_final=1e-10, max_steps=None):
+        steps = 0
+        while self.t < T_final * (1 + 1e-6):
+            self.step()
+            steps += 1
+            if max_steps is not None and steps >= max_steps:
+                break
+        return steps

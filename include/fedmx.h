@@ -1,0 +1,186 @@
+/*
+ * fedmx.h -- C ABI of the B200-native FEDM hot path (libfedmx.so).
+ *
+ * This is the drop-in boundary below the reference's L4 (fedm/functions.py, fedm/file_io.py): everything
+ * FEniCS 2019.1.0 / PETSc do underneath `nonlinear_solver.solve(problem, u_new.vector())`
+ * (reference: fedm/functions.py:1047) is reached through these entry points.  Each declaration cites the
+ * reference interface it replaces.  Conventions:
+ *   - plain C symbols, no exceptions cross the boundary; every call returns 0 on success and a negative
+ *     FEDMX_E* code otherwise, fedmx_last_error(ctx) returns the message;
+ *   - pointers named h_* are HOST pointers (set-up data, copied once), pointers named d_* are caller-owned
+ *     DEVICE pointers (e.g. torch tensors' data_ptr()); scalars are passed by value;
+ *   - all kernels are launched on the context's stream (fedmx_set_stream); calls that return host scalars
+ *     synchronise that stream, nothing else does;
+ *   - no allocation happens in per-step calls: device workspaces are sized in the set-up calls.
+ * Unknown layout: node-interleaved, dof = n_eq*node + comp (dolfin's mixed P1 layout); FP64 throughout,
+ * int32 indices.
+ */
+#ifndef FEDMX_H
+#define FEDMX_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fedmx_ctx fedmx_ctx;
+
+enum {
+    FEDMX_OK = 0,
+    FEDMX_EINVAL = -1,      /* bad argument / call order */
+    FEDMX_ECUDA = -2,       /* CUDA runtime error */
+    FEDMX_ENOMEM = -3,
+    FEDMX_ENCCL = -4,
+    FEDMX_EUNSUPPORTED = -5
+};
+
+/* model ids: which member of the FEDM form family the cell/facet kernels evaluate */
+enum {
+    FEDMX_MODEL_STREAMER = 1,   /* tests/integrated_tests/streamer_discharge/fedm_streamer.py:243-279 */
+    FEDMX_MODEL_TOF = 2,        /* tests/integrated_tests/time_of_flight/fedm_tof.py:120-127 */
+    FEDMX_MODEL_GLOW = 3,       /* tests/integrated_tests/glow_discharge/fedm_gd.py:349-385 */
+    FEDMX_MODEL_POISSON = 4     /* weak_form_Poisson_equation alone (initial potential), fedm_streamer.py:210-223 */
+};
+
+/* SNES convergence reasons (subset of PETSc's SNESConvergedReason the reference can observe) */
+enum {
+    FEDMX_SNES_CONVERGED_FNORM_ABS = 2,
+    FEDMX_SNES_CONVERGED_FNORM_RELATIVE = 3,
+    FEDMX_SNES_CONVERGED_SNORM_RELATIVE = 4,
+    FEDMX_SNES_DIVERGED_LINEAR_SOLVE = -3,
+    FEDMX_SNES_DIVERGED_FNORM_NAN = -4,
+    FEDMX_SNES_DIVERGED_MAX_IT = -5
+};
+
+/* ---- context ------------------------------------------------------------------------------------- */
+/* Replaces the implicit dolfin/PETSc global state created by `import dolfin` (fedm/functions.py:8). */
+int fedmx_ctx_create(int device, fedmx_ctx **out);
+int fedmx_ctx_destroy(fedmx_ctx *ctx);
+const char *fedmx_last_error(const fedmx_ctx *ctx);
+const char *fedmx_version(void);
+/* cudaStream_t passed as void*; NULL = the legacy default stream. */
+int fedmx_set_stream(fedmx_ctx *ctx, void *cuda_stream);
+
+/* ---- mesh, dof map, sparsity pattern (set-up, once) ------------------------------------------------ */
+/* Replaces dolfin Mesh/MeshFunction/DofMap/SparsityPattern construction behind
+ * `FunctionSpace(mesh, MixedElement([P1]*n_eq))` (fedm_streamer.py:141-143) and
+ * `Marking_boundaries` output consumption (fedm/functions.py:86-124).
+ * h_coords[n_vertices][2], h_cells[n_cells][3]; exterior facets: h_facet_vertices[n_facets][2],
+ * h_facet_marker[n_facets] (0 = unmarked, 1..15).  Only the locally owned rows -- the first n_owned
+ * vertices of the local numbering -- are assembled/stored (single GPU: n_owned = n_vertices); ghost
+ * vertices follow, and all cells touching an owned vertex must be present (one ghost-cell layer).  Builds the node graph, the BSR sparsity pattern (every cell-dof x
+ * cell-dof pair, as dolfin inserts them; blocks are stored even where the physics is zero), the
+ * SELL-32 storage and the per-row cell fans used by the assembly kernels. */
+int fedmx_mesh_set(fedmx_ctx *ctx, int n_eq, int64_t n_vertices, const double *h_coords,
+                   int64_t n_cells, const int32_t *h_cells,
+                   int64_t n_facets, const int32_t *h_facet_vertices, const int32_t *h_facet_marker,
+                   int64_t n_owned);
+/* Pattern queries (node-block CSR of the owned rows; expands to dolfin's scalar pattern with
+ * dof = n_eq*node+comp).  Call with NULL arrays to get sizes. */
+int fedmx_pattern_get(fedmx_ctx *ctx, int64_t *n_rows, int64_t *nnz_blocks, int32_t *h_rowptr, int32_t *h_colidx);
+/* Copy the assembled Jacobian out as block CSR values [nnz_blocks][n_eq][n_eq] (host buffer). */
+int fedmx_matrix_get_bsr(fedmx_ctx *ctx, double *h_values);
+
+/* Dirichlet conditions on one component: node list + index into the value table passed at solve time.
+ * Replaces `DirichletBC(ME.sub(k), value, subdomain)` (fedm_streamer.py:241, fedm_gd.py:345-347). */
+int fedmx_dirichlet_set(fedmx_ctx *ctx, int comp, int64_t n_nodes, const int32_t *h_nodes, const int32_t *h_value_index);
+
+/* ---- model (the "form compiler" output) ---------------------------------------------------------- */
+/* Replaces UFL form construction + FFC/dijitso JIT of `F = action(F,u_new); J = derivative(F,u_new,u)`
+ * (fedm_streamer.py:296-297): selects the hand-written cell/facet kernel family and its constants.
+ * h_params: model-specific double array (see fedm_b200/models.py for the layouts). */
+int fedmx_model_set(fedmx_ctx *ctx, int model_id, int n_params, const double *h_params);
+/* Per-node coefficient fields (P1 Functions: history terms, transport/rate coefficients...),
+ * d_fields[n_vertices][n_fields], caller-owned. */
+int fedmx_fields_bind(fedmx_ctx *ctx, int n_fields, const double *d_fields);
+
+/* ---- assembly (a1/a2: Problem.F / Problem.J, fedm/functions.py:188-202) --------------------------- */
+/* b = F(x) with Dirichlet rows b_i = x_i - g (assemble + bc.apply(b, x)); h_bc_values = value table. */
+int fedmx_assemble_residual(fedmx_ctx *ctx, const double *d_x, double dt, double dt_old, double t,
+                            const double *h_bc_values, int n_bc_values, double *d_b);
+/* A = dF/dx into the context's matrix storage, Dirichlet rows -> unit rows (assemble + bc.apply(A));
+ * if d_b != NULL the residual is produced in the same pass. */
+int fedmx_assemble_jacobian(fedmx_ctx *ctx, const double *d_x, double dt, double dt_old, double t,
+                            const double *h_bc_values, int n_bc_values, double *d_b);
+/* BDF2 history field hist = (-(1+w)^2 u_old + w^2 u_old1)/((1+w) dt), w = dt/dt_old
+ * (the u_old/u_old1 part of fedm/functions.py:356-357), for the first n_hist components. */
+int fedmx_bdf2_history(fedmx_ctx *ctx, int n_hist, const double *d_x_old, const double *d_x_old1,
+                       double dt, double dt_old, double *d_fields, int n_fields, int field_offset);
+
+/* ---- linear algebra (a15: PETSc Mat/Vec/KSP) -------------------------------------------------------- */
+int fedmx_spmv(fedmx_ctx *ctx, const double *d_x, double *d_y);               /* y = A x (MatMult) */
+int fedmx_norm2(fedmx_ctx *ctx, const double *d_x, int64_t n, double *out);   /* VecNorm(NORM_2) */
+int fedmx_dot(fedmx_ctx *ctx, const double *d_x, const double *d_y, int64_t n, double *out);
+/* GMRES(restart), left block-Jacobi preconditioning, classical Gram-Schmidt, convergence on the
+ * preconditioned residual: KSPGMRES + PCBJACOBI semantics (fedm_streamer.py:32 'gmres'). x starts at 0. */
+int fedmx_gmres(fedmx_ctx *ctx, const double *d_b, double *d_x, int restart, double rtol, double atol,
+                int max_it, int *iters, double *rnorm, int *converged);
+
+/* ---- Newton (a14: PETScSNESSolver.solve, fedm/functions.py:1047) ----------------------------------- */
+typedef struct {
+    double rtol, atol, stol;        /* SNES: relative_tolerance, absolute_tolerance (1e-10), solution tol (1e-16) */
+    int max_it;                     /* maximum_iterations */
+    int ksp_restart;                /* 30 */
+    double ksp_rtol, ksp_atol;      /* 1e-5, 1e-50 (PETSc defaults); tighten for 'mumps'-grade parity runs */
+    int ksp_max_it;                 /* 10000 */
+} fedmx_newton_params;
+
+typedef struct {
+    int iterations;                 /* Newton iterations */
+    int reason;                     /* FEDMX_SNES_* */
+    int linear_iterations;          /* total Krylov iterations */
+    double fnorm0, fnorm;           /* ||F(x0)||_2, final ||F||_2 */
+    double fnorm_history[64];
+} fedmx_newton_result;
+
+/* Solves F(x)=0 in place (d_x: initial guess in, solution out). Never throws: the host wrapper raises
+ * RuntimeError when reason < 0, which triggers the reference's retry path (fedm/functions.py:1080). */
+int fedmx_newton_solve(fedmx_ctx *ctx, double *d_x, double dt, double dt_old, double t,
+                       const double *h_bc_values, int n_bc_values,
+                       const fedmx_newton_params *params, fedmx_newton_result *result);
+
+/* ---- time-step control (a12/a13) ------------------------------------------------------------------- */
+/* err = ||a - b + eps||_2 / ||b + eps||_2 over component comp of two node-interleaved vectors
+ * (fedm/functions.py:1062-1064; eps = DOLFIN_EPS added entry-wise). */
+int fedmx_error_norm(fedmx_ctx *ctx, const double *d_new, const double *d_old, int comp, double eps, double *err);
+/* PID / PI.3.4 / H211b controllers (fedm/functions.py:915-951); host libm, bit-exact with the reference. */
+double fedmx_pid_step(double dt, const double err[3], double tol, double dt_min, double dt_max);
+double fedmx_pi34_step(double dt, const double err[3], double tol, double dt_min, double dt_max);
+double fedmx_h211b_step(double dt, double dt_old, const double err[3], double tol, double dt_min, double dt_max);
+
+/* ---- coefficient interpolation (a11: np.interp on dof vectors, fedm/functions.py:627-636, 739-747) - */
+/* out[i*out_stride] = np.interp(x[i*x_stride], kx, ky) / divisor for i < n (clamped, linear; the reference
+ * divides transport tables by N0, fedm/functions.py:627); tables are device arrays of n_table entries. */
+int fedmx_interp_table(fedmx_ctx *ctx, const double *d_x, int64_t x_stride, int64_t n,
+                       const double *d_kx, const double *d_ky, int n_table, double divisor,
+                       double *d_out, int64_t out_stride);
+
+/* ---- vector plumbing (a16: FunctionAssigner.assign / Function.assign) ----------------------------- */
+/* dst[i*dst_stride + dst_off] = src[i*src_stride + src_off], i < n (mixed <-> per-field split/merge). */
+int fedmx_strided_copy(fedmx_ctx *ctx, const double *d_src, int64_t src_stride, int64_t src_off,
+                       double *d_dst, int64_t dst_stride, int64_t dst_off, int64_t n);
+
+/* ---- multi-GPU (north_star (f): mesh partition, halo exchange, allreduce over NCCL) ---------------- */
+/* The host creates the id on rank 0 (fedmx_comm_unique_id), broadcasts the 128 bytes with its own
+ * plumbing (torch.distributed) and every rank calls fedmx_comm_init.  Replaces MPI inside dolfin/PETSc. */
+int fedmx_comm_unique_id(char id_out[128]);
+int fedmx_comm_init(fedmx_ctx *ctx, int n_ranks, int rank, const char id[128]);
+/* Halo plan: for every neighbour rank the owned nodes to send and the ghost nodes to receive
+ * (local node indices; CSR over neighbours). */
+int fedmx_halo_set(fedmx_ctx *ctx, int n_neighbors, const int32_t *h_neighbor_ranks,
+                   const int32_t *h_send_ptr, const int32_t *h_send_nodes,
+                   const int32_t *h_recv_ptr, const int32_t *h_recv_nodes);
+/* Ghost update of a node-interleaved vector with n_comp components per node (update_ghost_values(),
+ * fedm/functions.py:625; VecGhostUpdate inside MatMult). */
+int fedmx_halo_exchange(fedmx_ctx *ctx, double *d_vec, int n_comp);
+int fedmx_allreduce_sum(fedmx_ctx *ctx, double *d_buf, int n);
+
+/* ---- instrumentation ------------------------------------------------------------------------------- */
+/* Number of kernels this library launched since the last call with reset != 0. */
+int64_t fedmx_launch_count(fedmx_ctx *ctx, int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FEDMX_H */

@@ -1,0 +1,193 @@
+"""GPU parity tests of the streamer hot path against the CPU oracle (same seeded inputs), through the C ABI.
+
+Reference semantics: Problem.F / Problem.J (fedm/functions.py:188-202) for the forms of
+tests/integrated_tests/streamer_discharge/fedm_streamer.py, PETSc MatMult/KSP/SNES behind fedm/functions.py:1047,
+the estimator of fedm/functions.py:1062-1064 and the controller of :915-927.
+Tolerances: assembled entries 1e-12 relative to the largest entry of the same block row / residual component
+(entries are sums with cancellation, so a per-entry relative bound is not meaningful); states after N steps 1e-8.
+"""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+if not torch.cuda.is_available():
+    pytest.skip("needs a CUDA device", allow_module_level=True)
+
+from fedm_b200 import hotpath as hp
+from fedm_b200.streamer import StreamerCase, U_W
+from oracle.streamer import StreamerProblem, streamer_mesh as oracle_mesh
+from oracle.controller import error_estimate
+from oracle.newton import lu_solve
+
+
+def perturbed_state(prob, seed=0):
+    rng = np.random.default_rng(seed)
+    x0 = prob.initial_state()
+    X = x0.reshape(-1, 3).copy()
+    X[:, :2] += rng.normal(0, 1e-3, size=(X.shape[0], 2))
+    X[:, 2] += rng.normal(0, 1e-3 * U_W, size=X.shape[0])
+    Xo = X.copy()
+    Xo[:, :2] += rng.normal(0, 1e-3, size=(X.shape[0], 2))
+    Xo1 = Xo.copy()
+    Xo1[:, :2] += rng.normal(0, 1e-3, size=(X.shape[0], 2))
+    return X.ravel(), Xo.ravel(), Xo1.ravel()
+
+
+@pytest.fixture(scope="module", params=[(24, 1.0), (17, 2.0)])
+def setup(request):
+    n, p = request.param
+    prob = StreamerProblem(oracle_mesh(n, p))
+    case = StreamerCase(n=n, grading_power=p)
+    x, xo, xo1 = perturbed_state(prob)
+    dt, dt_old = 4e-12, 5e-12
+    prob.dt, prob.dt_old = dt, dt_old
+    prob.Uold, prob.Uold1 = xo.reshape(-1, 3), xo1.reshape(-1, 3)
+    dev = case.device
+    tx, txo, txo1 = (torch.from_numpy(v).to(dev) for v in (x, xo, xo1))
+    case.hot.bdf2_history(2, txo, txo1, dt, dt_old)
+    return prob, case, x, tx, dt, dt_old
+
+
+def bsr_to_csr(rowptr, colidx, vals, neq):
+    nb = rowptr.size - 1
+    A = sp.bsr_matrix((vals, colidx, rowptr), shape=(nb * neq, nb * neq)).tocsr()
+    A.sort_indices()
+    return A
+
+
+def test_pattern_is_dolfins(setup):
+    prob, case, *_ = setup
+    indptr, indices = prob.asm.pattern()
+    rowptr, colidx = case.hot.pattern()
+    ones = np.ones((colidx.size, 3, 3))
+    A = sp.bsr_matrix((ones, colidx, rowptr), shape=(prob.asm.ndof, prob.asm.ndof)).tocsr()
+    A.sort_indices()
+    assert np.array_equal(A.indptr, indptr)
+    assert np.array_equal(A.indices, indices)
+
+
+def test_residual_matches_oracle(setup):
+    """1e-12 relative to the size of the terms that are summed in each row, (|J| |x|)_i: the BDF2 term
+    e^u (c u - hist) cancels to ~1e-4 of its parts, so a bound relative to the net entry would only measure
+    that cancellation (the oracle and the kernel associate the sum differently)."""
+    prob, case, x, tx, dt, dt_old = setup
+    b_ref = prob.residual(x)
+    A_ref = prob.jacobian(x)
+    b = case.hot.residual(tx, dt, dt_old).cpu().numpy()
+    scale = np.abs(A_ref) @ np.abs(x)
+    ratio = np.abs(b - b_ref) / scale
+    print("residual max ratio", ratio.max(), "vs net", (np.abs(b - b_ref) / np.abs(b_ref).max()).max())
+    assert ratio.max() <= 1e-12
+    for k in range(3):
+        assert np.abs(b[k::3] - b_ref[k::3]).max() <= 1e-10 * np.abs(b_ref[k::3]).max(), k
+
+
+def test_jacobian_matches_oracle_and_is_deterministic(setup):
+    prob, case, x, tx, dt, dt_old = setup
+    A_ref = prob.jacobian(x)
+    case.hot.jacobian(tx, dt, dt_old)
+    rowptr, colidx, vals = case.hot.matrix_bsr()
+    A = bsr_to_csr(rowptr, colidx, vals, 3)
+    assert np.array_equal(A.indptr, A_ref.indptr) and np.array_equal(A.indices, A_ref.indices)
+    diff = np.abs(A.data - A_ref.data)
+    rowid = np.repeat(np.arange(A.shape[0]), np.diff(A.indptr))
+    rowmax = np.zeros(A.shape[0])
+    np.maximum.at(rowmax, rowid, np.abs(A_ref.data))
+    assert (diff <= 1e-12 * rowmax[rowid]).all(), float((diff / rowmax[rowid]).max())
+    # Dirichlet rows are unit rows
+    for d in prob.bc_dofs[:5]:
+        row = A.getrow(d).toarray().ravel()
+        assert row[d] == 1.0 and np.count_nonzero(row) == 1
+    # bit-reproducible (deterministic scatter)
+    case.hot.jacobian(tx, dt, dt_old)
+    _, _, vals2 = case.hot.matrix_bsr()
+    assert np.array_equal(vals, vals2)
+
+
+def test_spmv_and_gmres(setup):
+    prob, case, x, tx, dt, dt_old = setup
+    A_ref = prob.jacobian(x)
+    b_ref = prob.residual(x)
+    case.hot.jacobian(tx, dt, dt_old)
+    rng = np.random.default_rng(1)
+    v = rng.normal(size=x.size)
+    y = case.hot.spmv(torch.from_numpy(v).to(case.device)).cpu().numpy()
+    y_ref = A_ref @ v
+    rowscale = np.abs(A_ref) @ np.abs(v)
+    assert (np.abs(y - y_ref) <= 1e-13 * rowscale).all()
+    b = case.hot.residual(tx, dt, dt_old)
+    dx, its, conv, rn = case.hot.gmres(b, restart=30, rtol=1e-13, max_it=20000)
+    assert conv
+    dx_ref = lu_solve(A_ref, b_ref)
+    assert np.linalg.norm(dx.cpu().numpy() - dx_ref) <= 1e-8 * np.linalg.norm(dx_ref)
+    # reference-test semantics (rtol 1e-5): a handful of iterations, like PETSc's GMRES+ILU(0)
+    _, its5, conv5, _ = case.hot.gmres(b, restart=30, rtol=1e-5)
+    assert conv5 and its5 < 300
+
+
+def test_norms_and_error_estimator(setup):
+    prob, case, x, tx, dt, dt_old = setup
+    assert case.hot.norm2(tx) == pytest.approx(np.linalg.norm(x), rel=1e-14)
+    xo = prob.Uold.ravel()
+    txo = torch.from_numpy(xo).to(case.device)
+    e = case.hot.error_norm(tx, txo, 1)
+    assert e == pytest.approx(error_estimate(x[1::3], xo[1::3]), rel=1e-13)
+
+
+def test_full_run_matches_oracle():
+    """5 accepted steps from the same initial state, tight linear solves (the examples' 'mumps' semantics)."""
+    n = 32
+    prob = StreamerProblem(oracle_mesh(n))
+    x_ref, rows_ref, its_ref = prob.run(max_steps=5)
+    case = StreamerCase(n=n, ksp_rtol=1e-13, ksp_max_it=50000)
+    case.set_initial_state()
+    # initial Poisson solve on the device vs the oracle's LU
+    phi0 = prob.initial_state()[2::3]
+    assert np.abs(case.x_old.cpu().numpy()[2::3] - phi0).max() <= 1e-9 * np.abs(phi0).max()
+    case.run(max_steps=5)
+    x = case.x_new.cpu().numpy()
+    assert [s[0] for s in case.stats] == [h[0] for h in its_ref]          # same Newton iteration counts
+    for k in range(3):
+        ref = x_ref[k::3]
+        assert np.abs(x[k::3] - ref).max() <= 1e-8 * np.abs(ref).max(), k
+    for (e, a, b), (er, ar, br) in zip(case.rows, rows_ref):
+        assert a == ar and b == br
+        assert e == pytest.approx(er, rel=1e-7)
+
+
+def test_reference_test_semantics_run():
+    """GMRES at PETSc's default rtol 1e-5 (the streamer *test* setting): same Newton counts, same dt sequence,
+    estimator within 1e-6 of the exact-solve run."""
+    n = 32
+    prob = StreamerProblem(oracle_mesh(n))
+    _, rows_ref, its_ref = prob.run(max_steps=3)
+    case = StreamerCase(n=n)
+    case.set_initial_state()
+    case.run(max_steps=3)
+    assert [s[0] for s in case.stats] == [h[0] for h in its_ref]
+    for (e, a, b), (er, ar, br) in zip(case.rows, rows_ref):
+        assert a == ar and b == br
+        assert e == pytest.approx(er, rel=1e-6)
+
+
+def test_interp_and_strided_copy():
+    hot = hp.HotPath(0)
+    m = oracle_mesh(4)
+    hot.set_mesh(1, m.coords, m.cells)
+    rng = np.random.default_rng(3)
+    kx = np.sort(rng.uniform(0, 10, 353))
+    ky = rng.normal(size=353)
+    xq = np.concatenate([rng.uniform(-1, 11, 5000), kx[:10], [kx[0], kx[-1]]])
+    dev = hot.device
+    out = torch.empty(xq.size, dtype=torch.float64, device=dev)
+    hot.interp_table(torch.from_numpy(xq).to(dev), torch.from_numpy(kx).to(dev), torch.from_numpy(ky).to(dev), out,
+                     divisor=3.21877e22)
+    assert np.array_equal(out.cpu().numpy(), np.interp(xq, kx, ky) / 3.21877e22)      # bit-exact with numpy
+    src = torch.arange(30, dtype=torch.float64, device=dev)
+    dst = torch.zeros(10, dtype=torch.float64, device=dev)
+    hot.strided_copy(src, 3, 1, dst, 1, 0, 10)
+    assert np.array_equal(dst.cpu().numpy(), np.arange(30.0)[1::3])
+    hot.close()
