@@ -1,0 +1,254 @@
+#!/usr/bin/env python
+"""Headline benchmark: BDF2 steps/s (+ Jacobian-assembly GDOF/s) of the streamer case on a synthetic
+~10 M-DOF mesh (BASELINE.json `metric`), one process per GPU.
+
+    python bench.py --gpus N --steps K --warmup W            # this implementation
+    python bench.py --impl reference --steps K --warmup W    # CPU arm: the oracle port on the host cores
+
+One JSON line on stdout (rank 0).  A "step" is one accepted BDF2 time step of
+tests/integrated_tests/streamer_discharge/fedm_streamer.py:312-348 (state shift, Newton solve with
+GMRES(30)+block-Jacobi at PETSc's rtol 1e-5 -- the reference *test's* solver semantics --, error estimate,
+PID controller).  Inputs are larger than L2 (matrix 1.7 GB, vectors 80 MB each), no L2 flush needed.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+FULL_N = 1825            # n x n "right" grid -> 3 334 276 nodes, 10 002 828 DOF
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json, STREAM-style copy)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.lines, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def algorithmic_bytes(nv, nc, n_eq=3):
+    ne = nv + nc - 1                                  # Euler (planar, one boundary component)
+    nnzb = nv + 2 * ne
+    nnz = n_eq * n_eq * nnzb
+    asm = 12 * nc + 16 * nv + 3 * 8 * n_eq * nv + 8 * nnz + 8 * n_eq * nv
+    spmv = 8 * nnz + 4 * nnzb + 4 * nv + 16 * n_eq * nv                          # BSR-3 variant (SELL-32 block storage)
+    return asm, spmv, nnz
+
+
+# ---------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """CPU arm: the oracle port (C/OpenMP restatement when built, else the numpy oracle) on a bounded sample."""
+    from oracle import cpu_baseline
+    res = cpu_baseline.run(steps=args.steps, warmup=args.warmup, full_n=args.n, sample_n=args.sample_n)
+    line = {"impl": "reference", "metric": "streamer BDF2 steps/s (synthetic 10.0M-DOF mesh)", "value": res["value"],
+            "unit": "steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 / res["value"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"synthetic streamer mesh n={args.n} (right grid), BDF2 step, Newton rtol 1e-4, "
+                                   "GMRES(30) rtol 1e-5", "dof": 3 * (args.n + 1) ** 2},
+            "cpu_baseline": {"value": res["value"], "unit": "steps/s", "cores": res["cores"], "kind": res["kind"],
+                             "sample": res["sample"]},
+            "e2e": {"value": res["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="fedm_b200")
+    ap.add_argument("--n", type=int, default=FULL_N, help="grid size (n x n cells pairs); 1825 -> 10.0M DOF")
+    ap.add_argument("--sample-n", type=int, default=0, help="CPU-baseline sample grid (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank == 0:
+            run_reference(args)
+        return 0
+
+    import numpy as np
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from fedm_b200.streamer import StreamerCase
+
+    t_setup = time.time()
+    case = StreamerCase(n=args.n, device=local_rank, world=world, rank=rank)
+    case.set_initial_state(bench_initial_potential=True)
+    setup_s = time.time() - t_setup
+    hot = case.hot
+    nv, nc = case.global_vertices, case.global_cells
+    dof = 3 * nv
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        case.step()
+    # ---- timed region: K accepted steps, device-timed, max over ranks
+    hot.profile_enable(True)
+    hot.profile_get()
+    hot.launch_count(reset=True)
+    n_stats0 = len(case.stats)
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    attempts = 0
+    for _ in range(args.steps):
+        attempts += case.step()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clk = clocks.stop()
+    launches = hot.launch_count()
+    prof = hot.profile_get()
+    hot.profile_enable(False)
+    if world > 1:
+        tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    stats = case.stats[n_stats0:]
+    newton_its = sum(s[0] for s in stats)
+    krylov_its = sum(s[1] for s in stats)
+
+    # ---- end-to-end: same steps through the host-buffer API (H2D of the three state vectors, D2H of the result)
+    hb = case.make_host_buffers()
+    case.step_host(hb)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        case.step_host(hb)
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    if world > 1:
+        tms = torch.tensor([ms_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms_e2e = float(tms.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = peaks()
+    asm_b, spmv_b, nnz = algorithmic_bytes(nv, nc)
+    n_sp, ms_sp = prof["spmv"]
+    n_aj, ms_aj = prof["assemble_jacobian"]
+    n_ar, ms_ar = prof["assemble_residual"]
+    n_or, ms_or = prof["orthogonalisation"]
+    # per-rank algorithmic bytes (strong scaling: the mesh is split over the ranks)
+    spmv_gbs = (spmv_b / world) * n_sp / (ms_sp * 1e-3) / 1e9 if ms_sp > 0 else None
+    asm_gbs = (asm_b / world) * n_aj / (ms_aj * 1e-3) / 1e9 if ms_aj > 0 else None
+    line = {
+        "metric": "streamer BDF2 steps/s (synthetic 10.0M-DOF mesh)",
+        "value": args.steps / (ms * 1e-3), "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"synthetic streamer mesh n={args.n} (right grid), BDF2 step, Newton rtol 1e-4, "
+                               "GMRES(30)+block-Jacobi rtol 1e-5 (reference test semantics)",
+                   "dof": dof, "cells": nc, "nnz": nnz, "l2": "inputs larger than L2 (no flush)",
+                   "parallelism": f"vertex partition x{world}" if world > 1 else "single GPU"},
+        "attempts": attempts, "newton_its_per_step": newton_its / args.steps, "krylov_its_per_step": krylov_its / args.steps,
+        "jacobian_assembly_gdof_s": (dof * n_aj / (ms_aj * 1e-3) / 1e9) if ms_aj > 0 else None,
+        "residual_assembly_gdof_s": (dof * n_ar / (ms_ar * 1e-3) / 1e9) if ms_ar > 0 else None,
+        "kernel_ms_per_step": {"spmv": ms_sp / args.steps, "orthogonalisation": ms_or / args.steps,
+                               "assemble_jacobian": ms_aj / args.steps, "assemble_residual": ms_ar / args.steps},
+        "roofline": {"kernel": "spmv_kernel<3,true> (SELL-32 block SpMV + block-Jacobi)", "bound": "hbm",
+                     "achieved": spmv_gbs, "peak": peak, "unit": "GB/s", "frac": spmv_gbs / peak if spmv_gbs else None,
+                     "traffic": None, "peak_source": peak_src, "launches": n_sp,
+                     "algorithmic_bytes_per_launch": spmv_b / world},
+        "roofline_assembly": {"kernel": "assemble_rows_kernel<StreamerModel,true>", "bound": "hbm", "achieved": asm_gbs,
+                              "peak": peak, "unit": "GB/s", "frac": asm_gbs / peak if asm_gbs else None,
+                              "launches": n_aj, "algorithmic_bytes_per_launch": asm_b / world},
+        "e2e": {"value": args.steps / (ms_e2e * 1e-3), "unit": "steps/s",
+                "h2d_bytes_per_step": int(3 * 8 * dof), "d2h_bytes_per_step": int(8 * dof + 8)},
+        "gpu_launches": launches, "clocks": clk, "setup_s": setup_s,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            from oracle import cpu_baseline
+            res = cpu_baseline.run(steps=1, warmup=0, full_n=args.n, sample_n=args.sample_n)
+            line["cpu_baseline"] = {"value": res["value"], "unit": "steps/s", "cores": res["cores"], "kind": res["kind"],
+                                    "sample": res["sample"]}
+        except Exception as exc:                                # the baseline must never sink the GPU number
+            line["cpu_baseline"] = {"value": None, "unit": "steps/s", "cores": 0, "kind": "port", "sample": f"failed: {exc}"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

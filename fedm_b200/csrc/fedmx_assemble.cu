@@ -377,6 +377,7 @@ int launch_assembly(fedmx_ctx *ctx, const double *d_x, double *d_b, bool jac) {
     const int threads = 128;
     const int64_t rows = ctx->sell.n_slices * FEDMX_SLICE;
     const unsigned blocks = unsigned((rows + threads - 1) / threads);
+    ProfScope prof(ctx, jac ? FEDMX_PROF_ASM_JAC : FEDMX_PROF_ASM_RES);
     if (jac) assemble_rows_kernel<Model, true><<<blocks, threads, 0, ctx->stream>>>(A);
     else assemble_rows_kernel<Model, false><<<blocks, threads, 0, ctx->stream>>>(A);
     ctx->launches++;

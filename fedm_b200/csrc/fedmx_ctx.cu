@@ -26,6 +26,8 @@ extern "C" int fedmx_ctx_destroy(fedmx_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (void *p : ctx->owned_device) cudaFree(p);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    for (auto &pool : ctx->prof_ev)
+        for (cudaEvent_t e : pool) cudaEventDestroy(e);
     delete ctx;
     return FEDMX_OK;
 }
@@ -43,6 +45,47 @@ extern "C" int64_t fedmx_launch_count(fedmx_ctx *ctx, int reset) {
     int64_t n = ctx->launches;
     if (reset) ctx->launches = 0;
     return n;
+}
+
+// ---- profiling -----------------------------------------------------------------------------------------
+ProfScope::ProfScope(fedmx_ctx *ctx, int k) : c(ctx), kind(k) {
+    if (!c->prof_on) return;
+    auto &pool = c->prof_ev[kind];
+    if (c->prof_used[kind] + 2 > pool.size()) {
+        if (pool.size() >= 8192) fedmx_profile_flush(c, kind);
+        else
+            for (int i = 0; i < 256; ++i) { cudaEvent_t e; cudaEventCreate(&e); pool.push_back(e); }
+    }
+    cudaEvent_t start = pool[c->prof_used[kind]++];
+    stop = pool[c->prof_used[kind]++];
+    cudaEventRecord(start, c->stream);
+}
+ProfScope::~ProfScope() {
+    if (stop) { cudaEventRecord(stop, c->stream); c->prof_count[kind]++; }
+}
+int fedmx_profile_flush(fedmx_ctx *ctx, int kind) {
+    cudaStreamSynchronize(ctx->stream);
+    auto &pool = ctx->prof_ev[kind];
+    for (size_t i = 0; i + 1 < ctx->prof_used[kind]; i += 2) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, pool[i], pool[i + 1]) == cudaSuccess) ctx->prof_ms[kind] += ms;
+    }
+    ctx->prof_used[kind] = 0;
+    return FEDMX_OK;
+}
+extern "C" int fedmx_profile_enable(fedmx_ctx *ctx, int on) {
+    if (!ctx) return FEDMX_EINVAL;
+    ctx->prof_on = on != 0;
+    return FEDMX_OK;
+}
+extern "C" int fedmx_profile_get(fedmx_ctx *ctx, int kind, int64_t *count, double *total_ms) {
+    if (!ctx || kind < 0 || kind >= FEDMX_PROF_KINDS) return FEDMX_EINVAL;
+    fedmx_profile_flush(ctx, kind);
+    if (count) *count = ctx->prof_count[kind];
+    if (total_ms) *total_ms = ctx->prof_ms[kind];
+    ctx->prof_count[kind] = 0;
+    ctx->prof_ms[kind] = 0.0;
+    return FEDMX_OK;
 }
 
 // Step-size controllers: plain libm pow() so that the dt sequence is bit-identical to the reference's

@@ -93,6 +93,12 @@ struct fedmx_ctx {
     double *d_hess = nullptr;    // small device scalars for GMRES
     double *h_pinned = nullptr;  // pinned host scratch
     int64_t red_blocks = 0;
+    // profiling (CUDA events around kernel classes)
+    bool prof_on = false;
+    std::vector<cudaEvent_t> prof_ev[4];     // start/stop pairs per kind
+    size_t prof_used[4] = {0, 0, 0, 0};
+    int64_t prof_count[4] = {0, 0, 0, 0};
+    double prof_ms[4] = {0, 0, 0, 0};
     // comm
     void *nccl_comm = nullptr;
     int n_ranks = 1, rank = 0;
@@ -136,6 +142,16 @@ int fedmx_upload(fedmx_ctx *ctx, T **ptr, const std::vector<T> &h) {
     if (!h.empty()) FEDMX_CHECK_CUDA(ctx, cudaMemcpy(*ptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
     return FEDMX_OK;
 }
+
+// RAII helper: records an event pair around a group of launches when profiling is on
+struct ProfScope {
+    fedmx_ctx *c;
+    int kind;
+    cudaEvent_t stop = nullptr;
+    ProfScope(fedmx_ctx *ctx, int k);
+    ~ProfScope();
+};
+int fedmx_profile_flush(fedmx_ctx *ctx, int kind);
 
 // internal entry points shared between translation units
 int fedmx_ensure_workspace(fedmx_ctx *ctx, int restart);

@@ -355,6 +355,7 @@ int fedmx_update_block_jacobi(fedmx_ctx *ctx) {
 int fedmx_spmv_precond(fedmx_ctx *ctx, const double *d_x, double *d_y, bool precond) {
     const int threads = 128;
     const unsigned blocks = unsigned((ctx->sell.n_slices * FEDMX_SLICE + threads - 1) / threads);
+    ProfScope prof(ctx, FEDMX_PROF_SPMV);
 #define SPMV_CASE(N)                                                                                              \
     case N:                                                                                                       \
         if (precond) spmv_kernel<N, true><<<blocks, threads, 0, ctx->stream>>>(ctx->sell, ctx->d_val, ctx->d_dinv, d_x, d_y); \

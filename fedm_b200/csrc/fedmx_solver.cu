@@ -62,10 +62,13 @@ int gmres_impl(fedmx_ctx *ctx, const double *d_b, double *d_x, int restart, doub
             double *Vk = V + int64_t(k) * ld;
             if (multi && (rc = fedmx_halo_exchange_internal(ctx, Vk, ctx->n_eq))) return rc;
             if ((rc = fedmx_spmv_precond(ctx, Vk, w, true))) return rc;
-            if ((rc = fedmx_multidot(ctx, V, ld, k + 1, w, n, dh, false))) return rc;
-            if (multi && (rc = fedmx_global_sum(ctx, dh, k + 1))) return rc;
-            if ((rc = fedmx_multiaxpy_norm(ctx, V, ld, k + 1, dh, w, n, dh + 64))) return rc;
-            if (multi && (rc = fedmx_global_sum(ctx, dh + 64, 1))) return rc;
+            {
+                ProfScope prof(ctx, FEDMX_PROF_ORTHO);
+                if ((rc = fedmx_multidot(ctx, V, ld, k + 1, w, n, dh, false))) return rc;
+                if (multi && (rc = fedmx_global_sum(ctx, dh, k + 1))) return rc;
+                if ((rc = fedmx_multiaxpy_norm(ctx, V, ld, k + 1, dh, w, n, dh + 64))) return rc;
+                if (multi && (rc = fedmx_global_sum(ctx, dh + 64, 1))) return rc;
+            }
             // next basis vector: V_{k+1} = w / ||w||   (norm read on the device)
             if (k + 1 <= restart) {
                 if ((rc = fedmx_scale_copy(ctx, w, V + int64_t(k + 1) * ld, n, 1.0, nullptr))) return rc;

@@ -173,6 +173,18 @@ class HotPath:
     def launch_count(self, reset=False):
         return int(self.lib.fedmx_launch_count(self.h, 1 if reset else 0))
 
+    def profile_enable(self, on=True):
+        self._ck(self.lib.fedmx_profile_enable(self.h, 1 if on else 0))
+
+    def profile_get(self):
+        """{kind: (launches, total_ms)} since the last call, per kernel class (CUDA events on the stream)."""
+        out = {}
+        for kind, name in enumerate(("assemble_jacobian", "assemble_residual", "spmv", "orthogonalisation")):
+            n, ms = C.c_int64(), C.c_double()
+            self._ck(self.lib.fedmx_profile_get(self.h, kind, C.byref(n), C.byref(ms)))
+            out[name] = (n.value, ms.value)
+        return out
+
     # ---- multi-GPU ------------------------------------------------------------------------------------
     def comm_init(self, n_ranks, rank, unique_id):
         self._ck(self.lib.fedmx_comm_init(self.h, n_ranks, rank, unique_id))

@@ -63,6 +63,8 @@ SIGNATURES = {
     "fedmx_halo_exchange": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "fedmx_allreduce_sum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "fedmx_launch_count": (C.c_int64, [C.c_void_p, C.c_int]),
+    "fedmx_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
+    "fedmx_profile_get": (C.c_int, [C.c_void_p, C.c_int, c_i64p, c_dp]),
 }
 
 _lib = None

@@ -34,9 +34,12 @@ class StreamerCase:
     n_eq = 3
 
     def __init__(self, n=64, grading_power=1.0, device=0, mesh=None, newton_rtol=1e-4, newton_max_it=20,
-                 ksp_rtol=1e-5, ksp_restart=30, ksp_max_it=10000):
+                 ksp_rtol=1e-5, ksp_restart=30, ksp_max_it=10000, world=1, rank=0):
+        if world != 1:
+            raise NotImplementedError("partitioned runs are set up by fedm_b200.partition (see StreamerCase.partitioned)")
         self.mesh = mesh if mesh is not None else streamer_mesh(n, grading_power)
         m = self.mesh
+        self.global_vertices, self.global_cells = m.num_vertices, m.num_cells
         self.hot = hp.HotPath(device)
         fv = m.exterior_facets()
         self.hot.set_mesh(3, m.coords, m.cells, fv, m.mark_lines(BOUNDARIES))
@@ -69,7 +72,7 @@ class StreamerCase:
         ue = np.full_like(ui, np.log(1e13))
         return ui, ue
 
-    def solve_initial_potential(self, ui, ue, ksp_rtol=1e-13):
+    def solve_initial_potential(self, ui, ue, ksp_rtol=1e-13, ksp_max_it=200000, laplace_guess=False):
         m = self.mesh
         pot = hp.HotPath(self.device.index or 0)
         pot.set_mesh(1, m.coords, m.cells)
@@ -78,17 +81,25 @@ class StreamerCase:
         pot.set_model(hp.MODEL_POISSON, [ELEMENTARY_CHARGE / EPSILON_0], 2)
         pot.fields.copy_(torch.from_numpy(np.stack([ui, ue], axis=1)))
         phi = pot.new_vector()
-        res = pot.newton(phi, 1.0, 1.0, rtol=1e-12, atol=0.0, max_it=5, ksp_rtol=ksp_rtol, ksp_restart=60,
-                         ksp_max_it=200000)
+        if laplace_guess:
+            phi.copy_(torch.from_numpy(U_W * m.coords[:, 1] / BOX))
+        res = pot.newton(phi, 1.0, 1.0, rtol=1e-12, atol=0.0, max_it=5 if not laplace_guess else 1, ksp_rtol=ksp_rtol,
+                         ksp_restart=60, ksp_max_it=ksp_max_it, raise_on_failure=not laplace_guess)
         self.initial_poisson_stats = (res.iterations, res.linear_iterations, res.fnorm0, res.fnorm)
         out = phi.cpu().numpy()
         pot.close()
         return out
 
-    def set_initial_state(self, x0=None):
+    def set_initial_state(self, x0=None, bench_initial_potential=False):
+        """bench_initial_potential: start the (set-up only) Poisson solve from the Laplace field and stop it after a
+        bounded number of Krylov iterations -- Phi is an unknown of every coupled step, so the initial potential only
+        serves as Newton's first guess (it does not enter any form through u_old)."""
         if x0 is None:
             ui, ue = self.initial_log_densities()
-            phi = self.solve_initial_potential(ui, ue)
+            if bench_initial_potential:
+                phi = self.solve_initial_potential(ui, ue, ksp_rtol=1e-6, ksp_max_it=3000, laplace_guess=True)
+            else:
+                phi = self.solve_initial_potential(ui, ue)
             x0 = np.stack([ui, ue, phi], axis=1).ravel()
         x0 = torch.from_numpy(np.ascontiguousarray(x0)).to(self.device)
         self.x_new.copy_(x0)
@@ -102,9 +113,29 @@ class StreamerCase:
 
     # ---- one accepted step (fedm_streamer.py:313-348) -------------------------------------------------
     def step(self):
-        hot = self.hot
+        """u_old1 <- u_old <- u_new on the device (fedm_streamer.py:314-316), then solve."""
         self.x_old1.copy_(self.x_old)
         self.x_old.copy_(self.x_new)
+        return self._advance()
+
+    def make_host_buffers(self):
+        """Pinned host copies of the state, as the reference keeps them (PETSc vectors live in host memory)."""
+        mk = lambda t: t.detach().cpu().pin_memory()
+        return {"old": mk(self.x_new), "old1": mk(self.x_old), "new": mk(self.x_new)}
+
+    def step_host(self, hb):
+        """One step through host buffers: H2D of u_old and u_old1, solve, D2H of u_new (+ the scalar error)."""
+        self.x_old.copy_(hb["old"], non_blocking=True)
+        self.x_old1.copy_(hb["old1"], non_blocking=True)
+        self.x_new.copy_(self.x_old)
+        attempts = self._advance()
+        hb["new"].copy_(self.x_new, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        hb["old1"], hb["old"], hb["new"] = hb["old"], hb["new"], hb["old1"]
+        return attempts
+
+    def _advance(self):
+        hot = self.hot
 
         def solve_attempt(t_new, dt):
             hot.bdf2_history(2, self.x_old, self.x_old1, dt, self.dt_old)

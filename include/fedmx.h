@@ -179,6 +179,13 @@ int fedmx_allreduce_sum(fedmx_ctx *ctx, double *d_buf, int n);
 /* ---- instrumentation ------------------------------------------------------------------------------- */
 /* Number of kernels this library launched since the last call with reset != 0. */
 int64_t fedmx_launch_count(fedmx_ctx *ctx, int reset);
+/* Optional per-kernel-class device timing with CUDA events on the context's stream (used by bench.py for the
+ * roofline numbers).  kinds: 0 = Jacobian assembly, 1 = residual assembly, 2 = SpMV(+block-Jacobi),
+ * 3 = Gram-Schmidt multi-dot + multi-axpy.  fedmx_profile_get synchronises, returns launches and total ms
+ * since the last reset and resets the class. */
+enum { FEDMX_PROF_ASM_JAC = 0, FEDMX_PROF_ASM_RES = 1, FEDMX_PROF_SPMV = 2, FEDMX_PROF_ORTHO = 3, FEDMX_PROF_KINDS = 4 };
+int fedmx_profile_enable(fedmx_ctx *ctx, int on);
+int fedmx_profile_get(fedmx_ctx *ctx, int kind, int64_t *count, double *total_ms);
 
 #ifdef __cplusplus
 }
