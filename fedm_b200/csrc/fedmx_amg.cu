@@ -1,0 +1,277 @@
+// Two-stage preconditioner: algebraic multigrid V-cycle on the potential block + node-block Jacobi (sm_100a).
+//
+// The hierarchy (smoothed aggregation, fedm_b200/amg.py) is built once on the host -- the Phi-Phi block
+// 2 pi r grad(u).grad(v) (reference: fedm/functions.py:401) depends on the mesh only -- and uploaded level by
+// level; every operator (A_l, P_l, R_l) is stored in scalar SELL-32 so that all V-cycle kernels are coalesced,
+// HBM-bound streaming kernels (one thread per row).  Preconditioner application for r = (r_T, r_Phi):
+//     z   = Dinv r                       node-block Jacobi (transport part kept)
+//     rr  = r_Phi - A_{Phi,T} z_T        partial block SpMV (2 of n_eq^2 entry planes)
+//     z_Phi = Vcycle(rr)
+// i.e. a block lower-triangular (CPR-like) preconditioner.  PETSc's role here is PCApply inside KSPGMRES
+// (reference call site fedm/functions.py:1047); results do not depend on the preconditioner, only iteration counts.
+#include <algorithm>
+
+#include "fedmx_internal.h"
+
+namespace {
+
+enum { MODE_MULT = 0, MODE_RESID = 1, MODE_JACOBI = 2, MODE_ADD = 3 };
+
+template <int MODE>
+__global__ void __launch_bounds__(128) ssell_kernel(ScalarSell A, const double *__restrict__ x, const double *__restrict__ b,
+                                                    const double *__restrict__ dinv, double omega, double *__restrict__ y) {
+    const int64_t row = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t s = row / FEDMX_SLICE;
+    const int lane = int(row % FEDMX_SLICE);
+    if (s >= A.n_slices) return;
+    const int width = A.slice_width[s];
+    const int64_t base = A.slice_ptr[s] + lane;
+    double t = 0.0;
+    for (int k = 0; k < width; ++k) {
+        const int64_t e = base + int64_t(k) * FEDMX_SLICE;
+        t = fma(A.val[e], __ldg(x + A.col[e]), t);
+    }
+    if (row >= A.n_rows) return;
+    if (MODE == MODE_MULT) y[row] = t;
+    else if (MODE == MODE_RESID) y[row] = b[row] - t;
+    else if (MODE == MODE_JACOBI) y[row] = x[row] + omega * dinv[row] * (b[row] - t);
+    else y[row] += t;
+}
+
+__global__ void first_sweep_kernel(const double *__restrict__ b, const double *__restrict__ dinv, double omega,
+                                   double *__restrict__ x, int64_t n) {
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) x[i] = omega * dinv[i] * b[i];
+}
+
+// y = M b for a small dense M (n <= 4096): one warp per row
+__global__ void dense_matvec_kernel(const double *__restrict__ M, const double *__restrict__ b, double *__restrict__ y, int n) {
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    double acc = 0.0;
+    for (int j = lane; j < n; j += 32) acc = fma(M[int64_t(row) * n + j], b[j], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) y[row] = acc;
+}
+
+// rr[i] = r[NEQ*i+comp] - sum_j sum_{l != comp} A[(i,j)][comp][l] z[NEQ*j+l]     (owned columns only when local_only)
+template <int NEQ>
+__global__ void __launch_bounds__(128) phi_residual_kernel(SellView S, const double *__restrict__ val,
+                                                           const double *__restrict__ r, const double *__restrict__ z,
+                                                           int comp, int64_t n_local_cols, double *__restrict__ rr) {
+    constexpr int NB = NEQ * NEQ;
+    const int64_t row = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t s = row / FEDMX_SLICE;
+    const int lane = int(row % FEDMX_SLICE);
+    if (s >= S.n_slices) return;
+    const int width = S.slice_width[s];
+    const int64_t gbase = S.slice_ptr[s];
+    double acc = 0.0;
+    for (int k = 0; k < width; ++k) {
+        const int64_t slot = gbase + int64_t(k) * FEDMX_SLICE;
+        const int32_t c = S.col[slot + lane];
+        if (c >= n_local_cols) continue;
+        const double *v = val + slot * NB + lane;
+#pragma unroll
+        for (int l = 0; l < NEQ; ++l)
+            if (l != comp) acc = fma(__ldcs(v + (comp * NEQ + l) * FEDMX_SLICE), __ldg(z + int64_t(NEQ) * c + l), acc);
+    }
+    if (row < S.n_rows) rr[row] = r[int64_t(NEQ) * row + comp] - acc;
+}
+
+__global__ void comp_scatter_kernel(const double *__restrict__ e, double *__restrict__ z, int neq, int comp, int64_t n) {
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) z[int64_t(neq) * i + comp] = e[i];
+}
+
+int upload_ssell(fedmx_ctx *ctx, ScalarSell &M, int64_t n_rows, int64_t n_cols, const int32_t *rowptr, const int32_t *col,
+                 const double *val) {
+    M.n_rows = n_rows;
+    M.n_cols = n_cols;
+    M.n_slices = (n_rows + FEDMX_SLICE - 1) / FEDMX_SLICE;
+    std::vector<int64_t> sp(M.n_slices + 1, 0);
+    std::vector<int32_t> sw(M.n_slices, 0);
+    for (int64_t s = 0; s < M.n_slices; ++s) {
+        int w = 0;
+        for (int64_t r = s * FEDMX_SLICE; r < std::min<int64_t>(n_rows, (s + 1) * FEDMX_SLICE); ++r)
+            w = std::max(w, rowptr[r + 1] - rowptr[r]);
+        sw[s] = w;
+        sp[s + 1] = sp[s] + int64_t(w) * FEDMX_SLICE;
+    }
+    std::vector<int32_t> c(sp[M.n_slices], 0);
+    std::vector<double> v(sp[M.n_slices], 0.0);
+    for (int64_t r = 0; r < n_rows; ++r) {
+        const int64_t s = r / FEDMX_SLICE, l = r % FEDMX_SLICE;
+        for (int32_t q = rowptr[r]; q < rowptr[r + 1]; ++q) {
+            const int64_t e = sp[s] + int64_t(q - rowptr[r]) * FEDMX_SLICE + l;
+            c[e] = col[q];
+            v[e] = val[q];
+        }
+    }
+    int rc;
+    int64_t *dsp; int32_t *dsw, *dc; double *dv;
+    if ((rc = fedmx_upload(ctx, &dsp, sp))) return rc;
+    if ((rc = fedmx_upload(ctx, &dsw, sw))) return rc;
+    if ((rc = fedmx_upload(ctx, &dc, c))) return rc;
+    if ((rc = fedmx_upload(ctx, &dv, v))) return rc;
+    M.slice_ptr = dsp; M.slice_width = dsw; M.col = dc; M.val = dv;
+    return FEDMX_OK;
+}
+
+template <int MODE>
+void launch_ssell(fedmx_ctx *ctx, const ScalarSell &A, const double *x, const double *b, const double *dinv, double omega, double *y) {
+    const int threads = 128;
+    const unsigned blocks = unsigned((A.n_slices * FEDMX_SLICE + threads - 1) / threads);
+    ssell_kernel<MODE><<<blocks, threads, 0, ctx->stream>>>(A, x, b, dinv, omega, y);
+    ctx->launches++;
+}
+
+}  // namespace
+
+// One V-cycle with zero initial guess: x_0 = Vcycle(b_0); b_0 = levels[0].b, result in levels[0].x
+int fedmx_amg_vcycle(fedmx_ctx *ctx) {
+    auto &L = ctx->amg_levels;
+    const int nl = int(L.size());
+    FEDMX_REQUIRE(ctx, nl > 0 && ctx->amg_coarse_inv, "AMG hierarchy not set");
+    const int nu = ctx->amg_nu;
+    for (int l = 0; l < nl - 1; ++l) {
+        AmgLevel &lv = L[l];
+        const unsigned vb = unsigned((lv.n + 255) / 256);
+        first_sweep_kernel<<<vb, 256, 0, ctx->stream>>>(lv.b, lv.dinv, lv.omega, lv.x, lv.n);
+        ctx->launches++;
+        for (int sweep = 1; sweep < nu; ++sweep) {
+            launch_ssell<MODE_JACOBI>(ctx, lv.A, lv.x, lv.b, lv.dinv, lv.omega, lv.x2);
+            std::swap(lv.x, lv.x2);
+        }
+        launch_ssell<MODE_RESID>(ctx, lv.A, lv.x, lv.b, nullptr, 0.0, lv.r);
+        launch_ssell<MODE_MULT>(ctx, lv.R, lv.r, nullptr, nullptr, 0.0, L[l + 1].b);
+    }
+    {
+        AmgLevel &lc = L[nl - 1];
+        const int n = int(lc.n);
+        dense_matvec_kernel<<<(n * 32 + 127) / 128, 128, 0, ctx->stream>>>(ctx->amg_coarse_inv, lc.b, lc.x, n);
+        ctx->launches++;
+    }
+    for (int l = nl - 2; l >= 0; --l) {
+        AmgLevel &lv = L[l];
+        launch_ssell<MODE_ADD>(ctx, lv.P, L[l + 1].x, nullptr, nullptr, 0.0, lv.x);
+        for (int sweep = 0; sweep < nu; ++sweep) {
+            launch_ssell<MODE_JACOBI>(ctx, lv.A, lv.x, lv.b, lv.dinv, lv.omega, lv.x2);
+            std::swap(lv.x, lv.x2);
+        }
+    }
+    FEDMX_CHECK_CUDA(ctx, cudaGetLastError());
+    return FEDMX_OK;
+}
+
+int fedmx_apply_dinv(fedmx_ctx *ctx, const double *d_r, double *d_z);
+
+// z = M^-1 r  (r and z may not alias)
+int fedmx_precond_apply(fedmx_ctx *ctx, const double *d_r, double *d_z) {
+    int rc;
+    if (ctx->precond_kind == 0) return fedmx_apply_dinv(ctx, d_r, d_z);
+    ProfScope prof(ctx, FEDMX_PROF_PRECOND);
+    AmgLevel &l0 = ctx->amg_levels[0];
+    const int comp = ctx->amg_comp;
+    const int64_t n = ctx->n_owned;
+    const int threads = 128;
+    const unsigned blocks = unsigned((ctx->sell.n_slices * FEDMX_SLICE + threads - 1) / threads);
+    if (ctx->n_eq == 1) {
+        FEDMX_CHECK_CUDA(ctx, cudaMemcpyAsync(l0.b, d_r, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    } else {
+        if ((rc = fedmx_apply_dinv(ctx, d_r, d_z))) return rc;
+        switch (ctx->n_eq) {
+            case 3: phi_residual_kernel<3><<<blocks, threads, 0, ctx->stream>>>(ctx->sell, ctx->d_val, d_r, d_z, comp, n, l0.b); break;
+            case 5: phi_residual_kernel<5><<<blocks, threads, 0, ctx->stream>>>(ctx->sell, ctx->d_val, d_r, d_z, comp, n, l0.b); break;
+            default: ctx->err = "two-stage preconditioner: unsupported n_eq"; return FEDMX_EUNSUPPORTED;
+        }
+        ctx->launches++;
+    }
+    if ((rc = fedmx_amg_vcycle(ctx))) return rc;
+    comp_scatter_kernel<<<unsigned((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->amg_levels[0].x, d_z, ctx->n_eq, comp, n);
+    ctx->launches++;
+    FEDMX_CHECK_CUDA(ctx, cudaGetLastError());
+    return FEDMX_OK;
+}
+
+extern "C" int fedmx_amg_reset(fedmx_ctx *ctx) {
+    if (!ctx) return FEDMX_EINVAL;
+    ctx->amg_levels.clear();      // device memory stays owned by the context until destroy
+    ctx->amg_coarse_inv = nullptr;
+    ctx->precond_kind = 0;
+    return FEDMX_OK;
+}
+
+extern "C" int fedmx_amg_add_level(fedmx_ctx *ctx, int64_t n, const double *h_dinv, double omega, const int32_t *a_rowptr,
+                                   const int32_t *a_col, const double *a_val, int64_t n_coarse, const int32_t *p_rowptr,
+                                   const int32_t *p_col, const double *p_val, const int32_t *r_rowptr, const int32_t *r_col,
+                                   const double *r_val) {
+    if (!ctx) return FEDMX_EINVAL;
+    FEDMX_REQUIRE(ctx, n > 0 && h_dinv, "fedmx_amg_add_level: bad level");
+    FEDMX_REQUIRE(ctx, !ctx->amg_levels.empty() || n == ctx->n_owned, "fedmx_amg_add_level: finest level must have n_owned rows");
+    FEDMX_REQUIRE(ctx, ctx->amg_levels.empty() || ctx->amg_levels.back().n_coarse == n, "fedmx_amg_add_level: level sizes do not chain");
+    AmgLevel lv{};
+    lv.n = n;
+    lv.n_coarse = n_coarse;
+    lv.omega = omega;
+    int rc;
+    std::vector<double> d(h_dinv, h_dinv + n);
+    if ((rc = fedmx_upload(ctx, &lv.dinv, d))) return rc;
+    if ((rc = fedmx_dev_alloc(ctx, &lv.b, n))) return rc;
+    if ((rc = fedmx_dev_alloc(ctx, &lv.x, n))) return rc;
+    if ((rc = fedmx_dev_alloc(ctx, &lv.x2, n))) return rc;
+    if ((rc = fedmx_dev_alloc(ctx, &lv.r, n))) return rc;
+    if (n_coarse > 0) {
+        FEDMX_REQUIRE(ctx, a_rowptr && p_rowptr && r_rowptr, "fedmx_amg_add_level: missing operators");
+        if ((rc = upload_ssell(ctx, lv.A, n, n, a_rowptr, a_col, a_val))) return rc;
+        if ((rc = upload_ssell(ctx, lv.P, n, n_coarse, p_rowptr, p_col, p_val))) return rc;
+        if ((rc = upload_ssell(ctx, lv.R, n_coarse, n, r_rowptr, r_col, r_val))) return rc;
+    }
+    ctx->amg_levels.push_back(lv);
+    return FEDMX_OK;
+}
+
+extern "C" int fedmx_amg_set_coarse(fedmx_ctx *ctx, int n, const double *h_inverse) {
+    if (!ctx) return FEDMX_EINVAL;
+    FEDMX_REQUIRE(ctx, !ctx->amg_levels.empty() && ctx->amg_levels.back().n == n && ctx->amg_levels.back().n_coarse == 0,
+                  "fedmx_amg_set_coarse: the last level must be the coarsest one");
+    FEDMX_REQUIRE(ctx, n <= 8192, "fedmx_amg_set_coarse: coarsest level too large");
+    std::vector<double> m(h_inverse, h_inverse + size_t(n) * n);
+    return fedmx_upload(ctx, &ctx->amg_coarse_inv, m);
+}
+
+extern "C" int fedmx_precond_set(fedmx_ctx *ctx, int kind, int comp, int nu) {
+    if (!ctx) return FEDMX_EINVAL;
+    FEDMX_REQUIRE(ctx, kind == 0 || kind == 1, "fedmx_precond_set: kind must be 0 (block-Jacobi) or 1 (two-stage AMG)");
+    if (kind == 1) {
+        FEDMX_REQUIRE(ctx, !ctx->amg_levels.empty() && ctx->amg_coarse_inv, "fedmx_precond_set: upload the AMG hierarchy first");
+        FEDMX_REQUIRE(ctx, comp >= 0 && comp < ctx->n_eq && nu >= 1 && nu <= 4, "fedmx_precond_set: bad component / sweeps");
+    }
+    ctx->precond_kind = kind;
+    ctx->amg_comp = comp;
+    ctx->amg_nu = nu;
+    return FEDMX_OK;
+}
+
+// Entries (i,j) of every stored block, in block-CSR order (host buffer of nnz_blocks doubles).
+extern "C" int fedmx_matrix_get_component(fedmx_ctx *ctx, int i, int j, double *h_values) {
+    if (!ctx) return FEDMX_EINVAL;
+    FEDMX_REQUIRE(ctx, ctx->d_val && h_values && i >= 0 && j >= 0 && i < ctx->n_eq && j < ctx->n_eq, "fedmx_matrix_get_component: bad arguments");
+    const int NB = ctx->n_eq * ctx->n_eq;
+    const int e = i * ctx->n_eq + j;
+    const int64_t groups = ctx->sell.n_slots / FEDMX_SLICE;
+    std::vector<double> plane(size_t(ctx->sell.n_slots));
+    FEDMX_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    FEDMX_CHECK_CUDA(ctx, cudaMemcpy2D(plane.data(), FEDMX_SLICE * sizeof(double), ctx->d_val + int64_t(e) * FEDMX_SLICE,
+                                       size_t(NB) * FEDMX_SLICE * sizeof(double), FEDMX_SLICE * sizeof(double), groups,
+                                       cudaMemcpyDeviceToHost));
+    const auto &rp = ctx->h_rowptr;
+    for (int64_t r = 0; r < ctx->n_owned; ++r) {
+        const int64_t s = r / FEDMX_SLICE, l = r % FEDMX_SLICE;
+        for (int32_t q = rp[r]; q < rp[r + 1]; ++q)
+            h_values[q] = plane[int64_t(ctx->h_slice_ptr[s]) + int64_t(q - rp[r]) * FEDMX_SLICE + l];
+    }
+    return FEDMX_OK;
+}

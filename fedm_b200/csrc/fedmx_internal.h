@@ -52,6 +52,22 @@ struct ModelParams {
     double dt, dt_old, t;
 };
 
+// Scalar SELL-32 matrix (multigrid operators): entry (row r = 32 s + l, k) at slice_ptr[s] + 32 k + l
+struct ScalarSell {
+    int64_t n_rows = 0, n_cols = 0, n_slices = 0;
+    const int64_t *slice_ptr = nullptr;
+    const int32_t *slice_width = nullptr;
+    const int32_t *col = nullptr;
+    const double *val = nullptr;
+};
+
+struct AmgLevel {
+    int64_t n = 0, n_coarse = 0;
+    double omega = 1.0;
+    ScalarSell A, P, R;
+    double *dinv = nullptr, *b = nullptr, *x = nullptr, *x2 = nullptr, *r = nullptr;
+};
+
 struct HaloPlan {
     int n_neighbors = 0;
     std::vector<int> ranks;
@@ -93,12 +109,17 @@ struct fedmx_ctx {
     double *d_hess = nullptr;    // small device scalars for GMRES
     double *h_pinned = nullptr;  // pinned host scratch
     int64_t red_blocks = 0;
+    // preconditioner: 0 = node-block Jacobi, 1 = two-stage (AMG on component amg_comp + block Jacobi)
+    int precond_kind = 0, amg_comp = 0, amg_nu = 1;
+    std::vector<AmgLevel> amg_levels;
+    double *amg_coarse_inv = nullptr;
+    double *d_tmp = nullptr;
     // profiling (CUDA events around kernel classes)
     bool prof_on = false;
-    std::vector<cudaEvent_t> prof_ev[4];     // start/stop pairs per kind
-    size_t prof_used[4] = {0, 0, 0, 0};
-    int64_t prof_count[4] = {0, 0, 0, 0};
-    double prof_ms[4] = {0, 0, 0, 0};
+    std::vector<cudaEvent_t> prof_ev[5];     // start/stop pairs per kind
+    size_t prof_used[5] = {0, 0, 0, 0, 0};
+    int64_t prof_count[5] = {0, 0, 0, 0, 0};
+    double prof_ms[5] = {0, 0, 0, 0, 0};
     // comm
     void *nccl_comm = nullptr;
     int n_ranks = 1, rank = 0;
@@ -158,3 +179,4 @@ int fedmx_ensure_workspace(fedmx_ctx *ctx, int restart);
 int fedmx_update_block_jacobi(fedmx_ctx *ctx);
 int fedmx_spmv_precond(fedmx_ctx *ctx, const double *d_x, double *d_y, bool precond);
 int fedmx_norm2_local(fedmx_ctx *ctx, const double *d_x, int64_t n, double *out, bool global);
+int fedmx_precond_apply(fedmx_ctx *ctx, const double *d_r, double *d_z);

@@ -321,11 +321,13 @@ int fedmx_ensure_workspace(fedmx_ctx *ctx, int restart) {
         if ((rc = fedmx_dev_alloc(ctx, &ctx->d_res, n))) return rc;
         if ((rc = fedmx_dev_alloc(ctx, &ctx->d_dx, n))) return rc;
         if ((rc = fedmx_dev_alloc(ctx, &ctx->d_w, n))) return rc;
+        if ((rc = fedmx_dev_alloc(ctx, &ctx->d_tmp, n))) return rc;
         if ((rc = fedmx_dev_alloc(ctx, &ctx->d_red, size_t(kMaxRedBlocks) * 72))) return rc;
         if ((rc = fedmx_dev_alloc(ctx, &ctx->d_hess, 4096))) return rc;
         FEDMX_CHECK_CUDA(ctx, cudaMemset(ctx->d_res, 0, n * sizeof(double)));
         FEDMX_CHECK_CUDA(ctx, cudaMemset(ctx->d_dx, 0, n * sizeof(double)));
         FEDMX_CHECK_CUDA(ctx, cudaMemset(ctx->d_w, 0, n * sizeof(double)));
+        FEDMX_CHECK_CUDA(ctx, cudaMemset(ctx->d_tmp, 0, n * sizeof(double)));
         FEDMX_CHECK_CUDA(ctx, cudaMallocHost((void **)&ctx->h_pinned, 4096 * sizeof(double)));
     }
     if (restart > ctx->krylov_restart_alloc) {

@@ -39,8 +39,8 @@ int gmres_impl(fedmx_ctx *ctx, const double *d_b, double *d_x, int restart, doub
     auto Hm = [&](int i, int j) -> double & { return H[size_t(i) * restart + j]; };
 
     FEDMX_CHECK_CUDA(ctx, cudaMemsetAsync(d_x, 0, ld * sizeof(double), ctx->stream));
-    // r0 = Dinv b  (x0 = 0)
-    if ((rc = fedmx_apply_dinv(ctx, d_b, w))) return rc;
+    // r0 = M^-1 b  (x0 = 0)
+    if ((rc = fedmx_precond_apply(ctx, d_b, w))) return rc;
     double beta;
     if ((rc = fedmx_norm2_local(ctx, w, n, &beta, true))) return rc;
     const double tol = fmax(rtol * beta, atol);
@@ -61,7 +61,12 @@ int gmres_impl(fedmx_ctx *ctx, const double *d_b, double *d_x, int restart, doub
         for (int k = 0; k < restart && its < max_it; ++k) {
             double *Vk = V + int64_t(k) * ld;
             if (multi && (rc = fedmx_halo_exchange_internal(ctx, Vk, ctx->n_eq))) return rc;
-            if ((rc = fedmx_spmv_precond(ctx, Vk, w, true))) return rc;
+            if (ctx->precond_kind == 0) {
+                if ((rc = fedmx_spmv_precond(ctx, Vk, w, true))) return rc;       // block Jacobi fused into the SpMV epilogue
+            } else {
+                if ((rc = fedmx_spmv_precond(ctx, Vk, ctx->d_tmp, false))) return rc;
+                if ((rc = fedmx_precond_apply(ctx, ctx->d_tmp, w))) return rc;
+            }
             {
                 ProfScope prof(ctx, FEDMX_PROF_ORTHO);
                 if ((rc = fedmx_multidot(ctx, V, ld, k + 1, w, n, dh, false))) return rc;
@@ -115,9 +120,9 @@ int gmres_impl(fedmx_ctx *ctx, const double *d_b, double *d_x, int restart, doub
         if (its >= max_it) break;
         // restart: r = Dinv (b - A x)
         if (multi && (rc = fedmx_halo_exchange_internal(ctx, d_x, ctx->n_eq))) return rc;
-        if ((rc = fedmx_spmv_precond(ctx, d_x, w, false))) return rc;
-        if ((rc = fedmx_residual_from_ax(ctx, d_b, w, n))) return rc;
-        if ((rc = fedmx_apply_dinv(ctx, w, w))) return rc;
+        if ((rc = fedmx_spmv_precond(ctx, d_x, ctx->d_tmp, false))) return rc;
+        if ((rc = fedmx_residual_from_ax(ctx, d_b, ctx->d_tmp, n))) return rc;
+        if ((rc = fedmx_precond_apply(ctx, ctx->d_tmp, w))) return rc;
         if ((rc = fedmx_norm2_local(ctx, w, n, &beta, true))) return rc;
         rnorm = beta;
         if (beta <= tol) { *converged = 1; break; }

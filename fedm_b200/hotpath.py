@@ -103,6 +103,50 @@ class HotPath:
         self._ck(self.lib.fedmx_matrix_get_bsr(self.h, _np_ptr(vals)))
         return rowptr, colidx, vals
 
+    def matrix_component(self, i, j):
+        """Entry (i,j) of every stored block as a scipy CSR matrix (owned rows x local columns)."""
+        import scipy.sparse as sp
+        rowptr, colidx = self.pattern()
+        vals = np.empty(colidx.size)
+        self._ck(self.lib.fedmx_matrix_get_component(self.h, i, j, _np_ptr(vals)))
+        return sp.csr_matrix((vals, colidx, rowptr), shape=(self.n_owned, self.n_vertices))
+
+    def setup_two_stage_preconditioner(self, comp, bc_nodes, nu=1, theta=0.0):
+        """Builds the smoothed-aggregation hierarchy of the (state-independent) comp-comp block of the Jacobian that
+        is currently assembled on the device, uploads it and switches GMRES to the two-stage preconditioner."""
+        from . import amg
+        K = self.matrix_component(comp, comp)[:, :self.n_owned]
+        bc = np.asarray(bc_nodes, dtype=np.int64)
+        K = amg.symmetric_dirichlet(K, bc[bc < self.n_owned])
+        levels, coarse_inv = amg.build_hierarchy(K, theta=theta)
+        self._ck(self.lib.fedmx_amg_reset(self.h))
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        for l, lv in enumerate(levels):
+            A = lv["A"]
+            dinv = lv["dinv"].copy()
+            isolated = np.diff(A.indptr) == 1            # Dirichlet rows: make the damped sweep exact
+            dinv[isolated] = 1.0 / (lv["omega"] * A.diagonal()[isolated])
+            if "P" in lv:
+                P, R = lv["P"], lv["R"]
+                arrs = [i32(A.indptr), i32(A.indices), f64(A.data), i32(P.indptr), i32(P.indices), f64(P.data),
+                        i32(R.indptr), i32(R.indices), f64(R.data)]
+                self._ck(self.lib.fedmx_amg_add_level(self.h, A.shape[0], _np_ptr(f64(dinv)), float(lv["omega"]),
+                                                      _np_ptr(arrs[0]), _np_ptr(arrs[1]), _np_ptr(arrs[2]), P.shape[1],
+                                                      _np_ptr(arrs[3]), _np_ptr(arrs[4]), _np_ptr(arrs[5]),
+                                                      _np_ptr(arrs[6]), _np_ptr(arrs[7]), _np_ptr(arrs[8])))
+            else:
+                self._ck(self.lib.fedmx_amg_add_level(self.h, A.shape[0], _np_ptr(f64(dinv)), float(lv["omega"]),
+                                                      None, None, None, 0, None, None, None, None, None, None))
+        ci = f64(coarse_inv)
+        self._ck(self.lib.fedmx_amg_set_coarse(self.h, ci.shape[0], _np_ptr(ci)))
+        self._ck(self.lib.fedmx_precond_set(self.h, 1, comp, nu))
+        self.amg_levels = [lv["A"].shape[0] for lv in levels]
+        return self.amg_levels
+
+    def use_block_jacobi(self):
+        self._ck(self.lib.fedmx_precond_set(self.h, 0, 0, 1))
+
     def new_vector(self):
         return torch.zeros(self.n_vertices * self.n_eq, dtype=torch.float64, device=self.device)
 
@@ -179,7 +223,7 @@ class HotPath:
     def profile_get(self):
         """{kind: (launches, total_ms)} since the last call, per kernel class (CUDA events on the stream)."""
         out = {}
-        for kind, name in enumerate(("assemble_jacobian", "assemble_residual", "spmv", "orthogonalisation")):
+        for kind, name in enumerate(("assemble_jacobian", "assemble_residual", "spmv", "orthogonalisation", "preconditioner")):
             n, ms = C.c_int64(), C.c_double()
             self._ck(self.lib.fedmx_profile_get(self.h, kind, C.byref(n), C.byref(ms)))
             out[name] = (n.value, ms.value)

@@ -62,6 +62,12 @@ SIGNATURES = {
     "fedmx_halo_set": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fedmx_halo_exchange": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "fedmx_allreduce_sum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "fedmx_precond_set": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "fedmx_amg_reset": (C.c_int, [C.c_void_p]),
+    "fedmx_amg_add_level": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fedmx_amg_set_coarse": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "fedmx_matrix_get_component": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "fedmx_launch_count": (C.c_int64, [C.c_void_p, C.c_int]),
     "fedmx_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "fedmx_profile_get": (C.c_int, [C.c_void_p, C.c_int, c_i64p, c_dp]),

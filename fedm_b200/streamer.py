@@ -34,7 +34,7 @@ class StreamerCase:
     n_eq = 3
 
     def __init__(self, n=64, grading_power=1.0, device=0, mesh=None, newton_rtol=1e-4, newton_max_it=20,
-                 ksp_rtol=1e-5, ksp_restart=30, ksp_max_it=10000, world=1, rank=0):
+                 ksp_rtol=1e-5, ksp_restart=30, ksp_max_it=10000, world=1, rank=0, precond="amg"):
         if world != 1:
             raise NotImplementedError("partitioned runs are set up by fedm_b200.partition (see StreamerCase.partitioned)")
         self.mesh = mesh if mesh is not None else streamer_mesh(n, grading_power)
@@ -51,6 +51,16 @@ class StreamerCase:
         self.hot.set_dirichlet(2, self.bc_nodes, self.bc_index)
         self.hot.bc_values = np.array([0.0, U_W])
         self.hot.set_model(hp.MODEL_STREAMER, STREAMER_PARAMS, 2)
+        self.precond = precond
+        if precond == "amg":
+            # the Phi-Phi block does not depend on the state: assemble once at a harmless state (Laplace field)
+            x_lap = np.zeros((m.num_vertices, 3))
+            x_lap[:, :2] = np.log(1e13)
+            x_lap[:, 2] = U_W * m.coords[:, 1] / BOX
+            self.hot.jacobian(torch.from_numpy(x_lap.ravel()).to(self.hot.device), 5e-12, 1e30)
+            self.hot.setup_two_stage_preconditioner(2, self.bc_nodes)
+        elif precond != "bjacobi":
+            raise ValueError("precond must be 'amg' or 'bjacobi'")
         self.newton_kw = dict(rtol=newton_rtol, max_it=newton_max_it, ksp_rtol=ksp_rtol, ksp_restart=ksp_restart,
                               ksp_max_it=ksp_max_it)
         dev = self.hot.device
@@ -81,6 +91,9 @@ class StreamerCase:
         pot.set_model(hp.MODEL_POISSON, [ELEMENTARY_CHARGE / EPSILON_0], 2)
         pot.fields.copy_(torch.from_numpy(np.stack([ui, ue], axis=1)))
         phi = pot.new_vector()
+        if self.precond == "amg":
+            pot.jacobian(phi, 1.0, 1.0)
+            pot.setup_two_stage_preconditioner(0, self.bc_nodes)
         if laplace_guess:
             phi.copy_(torch.from_numpy(U_W * m.coords[:, 1] / BOX))
         res = pot.newton(phi, 1.0, 1.0, rtol=1e-12, atol=0.0, max_it=5 if not laplace_guess else 1, ksp_rtol=ksp_rtol,

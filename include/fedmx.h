@@ -112,10 +112,27 @@ int fedmx_bdf2_history(fedmx_ctx *ctx, int n_hist, const double *d_x_old, const 
 int fedmx_spmv(fedmx_ctx *ctx, const double *d_x, double *d_y);               /* y = A x (MatMult) */
 int fedmx_norm2(fedmx_ctx *ctx, const double *d_x, int64_t n, double *out);   /* VecNorm(NORM_2) */
 int fedmx_dot(fedmx_ctx *ctx, const double *d_x, const double *d_y, int64_t n, double *out);
-/* GMRES(restart), left block-Jacobi preconditioning, classical Gram-Schmidt, convergence on the
+/* GMRES(restart), left preconditioning (fedmx_precond_set), classical Gram-Schmidt, convergence on the
  * preconditioned residual: KSPGMRES + PCBJACOBI semantics (fedm_streamer.py:32 'gmres'). x starts at 0. */
 int fedmx_gmres(fedmx_ctx *ctx, const double *d_b, double *d_x, int restart, double rtol, double atol,
                 int max_it, int *iters, double *rnorm, int *converged);
+
+/* ---- preconditioner (PETSc PC behind KSP; the reference selects it with nonlinear_solver.parameters["preconditioner"],
+ * fedm_streamer.py:306-307) ----------------------------------------------------------------------------- */
+/* kind 0: node-block Jacobi (default).  kind 1: two-stage -- algebraic-multigrid V(nu,nu)-cycle on component `comp`
+ * (the potential: its block 2 pi r grad u . grad v, fedm/functions.py:401, depends on the mesh only) followed by
+ * node-block Jacobi on the other components; the hierarchy is built once by the host (fedm_b200/amg.py) and
+ * uploaded with fedmx_amg_add_level (finest first; host CSR arrays; P/R omitted on the coarsest level, whose dense
+ * inverse goes to fedmx_amg_set_coarse).  fedmx_matrix_get_component copies entry (i,j) of every stored block
+ * (block-CSR order) so that the host can extract that block from an assembled Jacobian. */
+int fedmx_precond_set(fedmx_ctx *ctx, int kind, int comp, int nu);
+int fedmx_amg_reset(fedmx_ctx *ctx);
+int fedmx_amg_add_level(fedmx_ctx *ctx, int64_t n, const double *h_dinv, double omega,
+                        const int32_t *a_rowptr, const int32_t *a_col, const double *a_val, int64_t n_coarse,
+                        const int32_t *p_rowptr, const int32_t *p_col, const double *p_val,
+                        const int32_t *r_rowptr, const int32_t *r_col, const double *r_val);
+int fedmx_amg_set_coarse(fedmx_ctx *ctx, int n, const double *h_inverse);
+int fedmx_matrix_get_component(fedmx_ctx *ctx, int i, int j, double *h_values);
 
 /* ---- Newton (a14: PETScSNESSolver.solve, fedm/functions.py:1047) ----------------------------------- */
 typedef struct {
@@ -181,9 +198,10 @@ int fedmx_allreduce_sum(fedmx_ctx *ctx, double *d_buf, int n);
 int64_t fedmx_launch_count(fedmx_ctx *ctx, int reset);
 /* Optional per-kernel-class device timing with CUDA events on the context's stream (used by bench.py for the
  * roofline numbers).  kinds: 0 = Jacobian assembly, 1 = residual assembly, 2 = SpMV(+block-Jacobi),
- * 3 = Gram-Schmidt multi-dot + multi-axpy.  fedmx_profile_get synchronises, returns launches and total ms
+ * 3 = Gram-Schmidt multi-dot + multi-axpy, 4 = two-stage preconditioner (block Jacobi + AMG V-cycle).  fedmx_profile_get synchronises, returns launches and total ms
  * since the last reset and resets the class. */
-enum { FEDMX_PROF_ASM_JAC = 0, FEDMX_PROF_ASM_RES = 1, FEDMX_PROF_SPMV = 2, FEDMX_PROF_ORTHO = 3, FEDMX_PROF_KINDS = 4 };
+enum { FEDMX_PROF_ASM_JAC = 0, FEDMX_PROF_ASM_RES = 1, FEDMX_PROF_SPMV = 2, FEDMX_PROF_ORTHO = 3, FEDMX_PROF_PRECOND = 4,
+       FEDMX_PROF_KINDS = 5 };
 int fedmx_profile_enable(fedmx_ctx *ctx, int on);
 int fedmx_profile_get(fedmx_ctx *ctx, int kind, int64_t *count, double *total_ms);
 
