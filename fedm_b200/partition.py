@@ -1,0 +1,87 @@
+"""Vertex partition of a triangle mesh across GPUs, ghost layer and halo plan (host, set-up only).
+
+Mirrors what dolfin's MPI mesh decomposition provides to the reference under ``mpirun -np N`` (README.md:63-67 of
+the reference): every rank owns a contiguous chunk of vertices (strips along one axis), keeps all cells touching
+an owned vertex (one ghost-cell layer), so residual/Jacobian assembly is owner-computes with no communication;
+ghost values of a vector are refreshed by one halo exchange (``update_ghost_values()``, fedm/functions.py:625).
+Local numbering: owned vertices first (ascending global id), ghosts after (ascending global id).
+"""
+import numpy as np
+
+
+class LocalMesh:
+    """One rank's view: local coords/cells/facets + maps to the global numbering + its halo plan."""
+
+    def __init__(self, rank, world, coords, cells, n_owned, local_to_global, facet_vertices, facet_markers,
+                 neighbors, send_ptr, send_nodes, recv_ptr, recv_nodes, n_global_vertices, n_global_cells):
+        self.rank, self.world = rank, world
+        self.coords, self.cells, self.n_owned = coords, cells, n_owned
+        self.local_to_global = local_to_global
+        self.facet_vertices, self.facet_markers = facet_vertices, facet_markers
+        self.neighbors, self.send_ptr, self.send_nodes = neighbors, send_ptr, send_nodes
+        self.recv_ptr, self.recv_nodes = recv_ptr, recv_nodes
+        self.n_global_vertices, self.n_global_cells = n_global_vertices, n_global_cells
+
+    @property
+    def num_vertices(self):
+        return self.coords.shape[0]
+
+    def global_to_local(self):
+        g2l = np.full(self.n_global_vertices, -1, dtype=np.int64)
+        g2l[self.local_to_global] = np.arange(self.local_to_global.size)
+        return g2l
+
+
+def strip_owner(coords, world, axis=1):
+    """Owner rank per vertex: vertices sorted by (coords[axis], other axis) and cut into `world` equal chunks."""
+    n = coords.shape[0]
+    order = np.lexsort((coords[:, 1 - axis], coords[:, axis]))
+    owner = np.empty(n, dtype=np.int32)
+    bounds = (np.arange(world + 1) * n) // world
+    for p in range(world):
+        owner[order[bounds[p]:bounds[p + 1]]] = p
+    return owner
+
+
+def build_local_mesh(coords, cells, facet_vertices, facet_markers, owner, rank, world):
+    n = coords.shape[0]
+    cells = np.asarray(cells)
+    owned = np.nonzero(owner == rank)[0]
+    touch = (owner[cells] == rank).any(axis=1)
+    lcells_g = cells[touch]
+    verts = np.unique(lcells_g)
+    ghosts = verts[owner[verts] != rank]
+    l2g = np.concatenate([owned, ghosts]).astype(np.int64)
+    g2l = np.full(n, -1, dtype=np.int64)
+    g2l[l2g] = np.arange(l2g.size)
+    lcells = g2l[lcells_g].astype(np.int32)
+    fv = np.asarray(facet_vertices).reshape(-1, 2)
+    keep = (g2l[fv] >= 0).all(axis=1) if fv.size else np.zeros(0, dtype=bool)
+    lfv = g2l[fv[keep]].astype(np.int32)
+    lfm = np.asarray(facet_markers)[keep].astype(np.int32) if fv.size else np.zeros(0, dtype=np.int32)
+    # ---- halo plan: what I receive (my ghosts, grouped by owner) and what I send (my owned nodes that are ghosts elsewhere)
+    recv_by = {}
+    for q in np.unique(owner[ghosts]):
+        recv_by[int(q)] = ghosts[owner[ghosts] == q]                      # ascending global id
+    send_by = {}
+    for q in range(world):
+        if q == rank:
+            continue
+        touch_q = (owner[cells] == q).any(axis=1)
+        vq = np.unique(cells[touch_q])
+        mine = vq[owner[vq] == rank]
+        if mine.size:
+            send_by[q] = mine                                             # ascending global id == q's recv order
+    neighbors = sorted(set(recv_by) | set(send_by))
+    send_ptr, recv_ptr, send_nodes, recv_nodes = [0], [0], [], []
+    for q in neighbors:
+        s = send_by.get(q, np.zeros(0, dtype=np.int64))
+        r = recv_by.get(q, np.zeros(0, dtype=np.int64))
+        send_nodes.append(g2l[s])
+        recv_nodes.append(g2l[r])
+        send_ptr.append(send_ptr[-1] + s.size)
+        recv_ptr.append(recv_ptr[-1] + r.size)
+    cat = lambda parts: (np.concatenate(parts) if parts else np.zeros(0)).astype(np.int32)
+    return LocalMesh(rank, world, np.ascontiguousarray(coords[l2g]), lcells, owned.size, l2g, lfv, lfm,
+                     np.asarray(neighbors, dtype=np.int32), np.asarray(send_ptr, dtype=np.int32), cat(send_nodes),
+                     np.asarray(recv_ptr, dtype=np.int32), cat(recv_nodes), n, cells.shape[0])

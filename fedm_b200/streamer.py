@@ -35,14 +35,23 @@ class StreamerCase:
 
     def __init__(self, n=64, grading_power=1.0, device=0, mesh=None, newton_rtol=1e-4, newton_max_it=20,
                  ksp_rtol=1e-5, ksp_restart=30, ksp_max_it=10000, world=1, rank=0, precond="amg"):
-        if world != 1:
-            raise NotImplementedError("partitioned runs are set up by fedm_b200.partition (see StreamerCase.partitioned)")
-        self.mesh = mesh if mesh is not None else streamer_mesh(n, grading_power)
-        m = self.mesh
-        self.global_vertices, self.global_cells = m.num_vertices, m.num_cells
+        gmesh = mesh if mesh is not None else streamer_mesh(n, grading_power)
+        self.global_vertices, self.global_cells = gmesh.num_vertices, gmesh.num_cells
+        self.world, self.rank = world, rank
+        fv = gmesh.exterior_facets()
+        fm = gmesh.mark_lines(BOUNDARIES)
         self.hot = hp.HotPath(device)
-        fv = m.exterior_facets()
-        self.hot.set_mesh(3, m.coords, m.cells, fv, m.mark_lines(BOUNDARIES))
+        if world == 1:
+            self.mesh = m = gmesh
+            self.local = None
+            self.hot.set_mesh(3, m.coords, m.cells, fv, fm)
+        else:
+            from .partition import build_local_mesh, strip_owner
+            owner = strip_owner(gmesh.coords, world, axis=1)
+            self.local = m = build_local_mesh(gmesh.coords, gmesh.cells, fv, fm, owner, rank, world)
+            self.mesh = m
+            self.hot.set_mesh(3, m.coords, m.cells, m.facet_vertices, m.facet_markers, n_owned=m.n_owned)
+            self._comm_setup(self.hot)
         z = m.coords[:, 1]
         cath = np.nonzero(np.abs(z) < 3e-16)[0]
         anod = np.nonzero(np.abs(z - BOX) < 3e-16)[0]
@@ -75,6 +84,20 @@ class StreamerCase:
         self.stats = []
         self.device = dev
 
+    def _comm_setup(self, hot):
+        """One NCCL communicator per context: rank 0 creates the id, torch.distributed carries the 128 bytes."""
+        import ctypes
+        import torch.distributed as dist
+        buf = ctypes.create_string_buffer(128)
+        if self.rank == 0:
+            hot._ck(hot.lib.fedmx_comm_unique_id(buf))
+        t = torch.tensor(list(buf.raw), dtype=torch.uint8, device=hot.device)
+        dist.broadcast(t, 0)
+        ident = bytes(t.cpu().tolist())
+        hot.comm_init(self.world, self.rank, ident)
+        lm = self.local
+        hot.set_halo(lm.neighbors, lm.send_ptr, lm.send_nodes, lm.recv_ptr, lm.recv_nodes)
+
     # ---- initial condition + initial Poisson solve ---------------------------------------------------
     def initial_log_densities(self):
         r, z = self.mesh.coords[:, 0], self.mesh.coords[:, 1]
@@ -85,7 +108,11 @@ class StreamerCase:
     def solve_initial_potential(self, ui, ue, ksp_rtol=1e-13, ksp_max_it=200000, laplace_guess=False):
         m = self.mesh
         pot = hp.HotPath(self.device.index or 0)
-        pot.set_mesh(1, m.coords, m.cells)
+        if self.world == 1:
+            pot.set_mesh(1, m.coords, m.cells)
+        else:
+            pot.set_mesh(1, m.coords, m.cells, n_owned=m.n_owned)
+            self._comm_setup(pot)
         pot.set_dirichlet(0, self.bc_nodes, self.bc_index)
         pot.bc_values = np.array([0.0, U_W])
         pot.set_model(hp.MODEL_POISSON, [ELEMENTARY_CHARGE / EPSILON_0], 2)
