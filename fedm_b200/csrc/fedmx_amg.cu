@@ -13,6 +13,9 @@
 
 #include "fedmx_internal.h"
 
+int fedmx_halo_exchange_internal(fedmx_ctx *ctx, double *d_vec, int n_comp);
+int fedmx_global_sum(fedmx_ctx *ctx, double *d_buf, int n);
+
 namespace {
 
 enum { MODE_MULT = 0, MODE_RESID = 1, MODE_JACOBI = 2, MODE_ADD = 3 };
@@ -142,11 +145,18 @@ int fedmx_amg_vcycle(fedmx_ctx *ctx) {
         first_sweep_kernel<<<vb, 256, 0, ctx->stream>>>(lv.b, lv.dinv, lv.omega, lv.x, lv.n);
         ctx->launches++;
         for (int sweep = 1; sweep < nu; ++sweep) {
+            int rc;
+            if (l == 0 && ctx->n_ranks > 1 && (rc = fedmx_halo_exchange_internal(ctx, lv.x, 1))) return rc;
             launch_ssell<MODE_JACOBI>(ctx, lv.A, lv.x, lv.b, lv.dinv, lv.omega, lv.x2);
             std::swap(lv.x, lv.x2);
         }
+        const bool dist = (l == 0 && ctx->n_ranks > 1);
+        int rc;
+        if (dist && (rc = fedmx_halo_exchange_internal(ctx, lv.x, 1))) return rc;      // ghosts of x for A x
         launch_ssell<MODE_RESID>(ctx, lv.A, lv.x, lv.b, nullptr, 0.0, lv.r);
         launch_ssell<MODE_MULT>(ctx, lv.R, lv.r, nullptr, nullptr, 0.0, L[l + 1].b);
+        // distributed fine level: R holds only this rank's fine columns; the coarse right-hand side is the sum over ranks
+        if (dist && (rc = fedmx_global_sum(ctx, L[l + 1].b, int(L[l + 1].n)))) return rc;
     }
     {
         AmgLevel &lc = L[nl - 1];
@@ -158,6 +168,8 @@ int fedmx_amg_vcycle(fedmx_ctx *ctx) {
         AmgLevel &lv = L[l];
         launch_ssell<MODE_ADD>(ctx, lv.P, L[l + 1].x, nullptr, nullptr, 0.0, lv.x);
         for (int sweep = 0; sweep < nu; ++sweep) {
+            int rc;
+            if (l == 0 && ctx->n_ranks > 1 && (rc = fedmx_halo_exchange_internal(ctx, lv.x, 1))) return rc;
             launch_ssell<MODE_JACOBI>(ctx, lv.A, lv.x, lv.b, lv.dinv, lv.omega, lv.x2);
             std::swap(lv.x, lv.x2);
         }
@@ -182,9 +194,11 @@ int fedmx_precond_apply(fedmx_ctx *ctx, const double *d_r, double *d_z) {
         FEDMX_CHECK_CUDA(ctx, cudaMemcpyAsync(l0.b, d_r, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     } else {
         if ((rc = fedmx_apply_dinv(ctx, d_r, d_z))) return rc;
+        if (ctx->n_ranks > 1 && (rc = fedmx_halo_exchange_internal(ctx, d_z, ctx->n_eq))) return rc;
+        const int64_t ncols = ctx->n_vertices;
         switch (ctx->n_eq) {
-            case 3: phi_residual_kernel<3><<<blocks, threads, 0, ctx->stream>>>(ctx->sell, ctx->d_val, d_r, d_z, comp, n, l0.b); break;
-            case 5: phi_residual_kernel<5><<<blocks, threads, 0, ctx->stream>>>(ctx->sell, ctx->d_val, d_r, d_z, comp, n, l0.b); break;
+            case 3: phi_residual_kernel<3><<<blocks, threads, 0, ctx->stream>>>(ctx->sell, ctx->d_val, d_r, d_z, comp, ncols, l0.b); break;
+            case 5: phi_residual_kernel<5><<<blocks, threads, 0, ctx->stream>>>(ctx->sell, ctx->d_val, d_r, d_z, comp, ncols, l0.b); break;
             default: ctx->err = "two-stage preconditioner: unsupported n_eq"; return FEDMX_EUNSUPPORTED;
         }
         ctx->launches++;
@@ -219,10 +233,16 @@ extern "C" int fedmx_amg_add_level(fedmx_ctx *ctx, int64_t n, const double *h_di
     int rc;
     std::vector<double> d(h_dinv, h_dinv + n);
     if ((rc = fedmx_upload(ctx, &lv.dinv, d))) return rc;
-    if ((rc = fedmx_dev_alloc(ctx, &lv.b, n))) return rc;
-    if ((rc = fedmx_dev_alloc(ctx, &lv.x, n))) return rc;
-    if ((rc = fedmx_dev_alloc(ctx, &lv.x2, n))) return rc;
-    if ((rc = fedmx_dev_alloc(ctx, &lv.r, n))) return rc;
+    // the finest level of a partitioned run carries ghost entries (columns of A beyond the owned rows)
+    const int64_t nvec = ctx->amg_levels.empty() ? std::max<int64_t>(n, ctx->n_vertices) : n;
+    if ((rc = fedmx_dev_alloc(ctx, &lv.b, nvec))) return rc;
+    if ((rc = fedmx_dev_alloc(ctx, &lv.x, nvec))) return rc;
+    if ((rc = fedmx_dev_alloc(ctx, &lv.x2, nvec))) return rc;
+    if ((rc = fedmx_dev_alloc(ctx, &lv.r, nvec))) return rc;
+    FEDMX_CHECK_CUDA(ctx, cudaMemset(lv.b, 0, nvec * sizeof(double)));
+    FEDMX_CHECK_CUDA(ctx, cudaMemset(lv.x, 0, nvec * sizeof(double)));
+    FEDMX_CHECK_CUDA(ctx, cudaMemset(lv.x2, 0, nvec * sizeof(double)));
+    FEDMX_CHECK_CUDA(ctx, cudaMemset(lv.r, 0, nvec * sizeof(double)));
     if (n_coarse > 0) {
         FEDMX_REQUIRE(ctx, a_rowptr && p_rowptr && r_rowptr, "fedmx_amg_add_level: missing operators");
         if ((rc = upload_ssell(ctx, lv.A, n, n, a_rowptr, a_col, a_val))) return rc;

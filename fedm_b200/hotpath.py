@@ -111,24 +111,66 @@ class HotPath:
         self._ck(self.lib.fedmx_matrix_get_component(self.h, i, j, _np_ptr(vals)))
         return sp.csr_matrix((vals, colidx, rowptr), shape=(self.n_owned, self.n_vertices))
 
-    def setup_two_stage_preconditioner(self, comp, bc_nodes, nu=1, theta=0.0):
+    def setup_two_stage_preconditioner(self, comp, bc_nodes, nu=1, theta=0.0, local_mesh=None):
         """Builds the smoothed-aggregation hierarchy of the (state-independent) comp-comp block of the Jacobian that
-        is currently assembled on the device, uploads it and switches GMRES to the two-stage preconditioner."""
+        is currently assembled on the device, uploads it and switches GMRES to the two-stage preconditioner.
+        Partitioned runs (local_mesh given): the owned rows of all ranks are gathered into the global block, every
+        rank builds the identical global hierarchy, keeps its own slice of the finest level (halo exchange per
+        smoothing step) and a replica of all coarser levels (the restricted residual is all-reduced)."""
+        import scipy.sparse as sp
         from . import amg
-        K = self.matrix_component(comp, comp)[:, :self.n_owned]
+        Kloc = self.matrix_component(comp, comp)
         bc = np.asarray(bc_nodes, dtype=np.int64)
-        K = amg.symmetric_dirichlet(K, bc[bc < self.n_owned])
-        levels, coarse_inv = amg.build_hierarchy(K, theta=theta)
-        self._ck(self.lib.fedmx_amg_reset(self.h))
         i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
         f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        if local_mesh is None or local_mesh.world == 1:
+            K = amg.symmetric_dirichlet(Kloc[:, :self.n_owned], bc[bc < self.n_owned])
+            levels, coarse_inv = amg.build_hierarchy(K, theta=theta)
+            fine_ops = None
+        else:
+            import torch.distributed as dist
+            lm = local_mesh
+            l2g = lm.local_to_global
+            coo = Kloc.tocoo()
+            trip = torch.from_numpy(np.stack([l2g[coo.row].astype(np.float64), l2g[coo.col].astype(np.float64), coo.data])).to(self.device)
+            sizes = [torch.zeros(1, dtype=torch.int64, device=self.device) for _ in range(lm.world)]
+            dist.all_gather(sizes, torch.tensor([trip.shape[1]], dtype=torch.int64, device=self.device))
+            mx = int(max(int(t.item()) for t in sizes))
+            pad = torch.zeros((3, mx), dtype=torch.float64, device=self.device)
+            pad[:, :trip.shape[1]] = trip
+            bufs = [torch.empty_like(pad) for _ in range(lm.world)]
+            dist.all_gather(bufs, pad)
+            parts = [b[:, :int(sz.item())].cpu().numpy() for b, sz in zip(bufs, sizes)]
+            allt = np.concatenate(parts, axis=1)
+            ng = lm.n_global_vertices
+            Kg = sp.csr_matrix((allt[2], (allt[0].astype(np.int64), allt[1].astype(np.int64))), shape=(ng, ng))
+            bcg = torch.zeros(ng, dtype=torch.float64, device=self.device)
+            bcg[torch.from_numpy(l2g[bc[bc < self.n_owned]]).to(self.device)] = 1.0
+            dist.all_reduce(bcg)
+            Kg = amg.symmetric_dirichlet(Kg, np.nonzero(bcg.cpu().numpy() > 0)[0])
+            levels, coarse_inv = amg.build_hierarchy(Kg, theta=theta)
+            owned_g = l2g[:self.n_owned]
+            g2l = lm.global_to_local()
+            A0 = levels[0]["A"][owned_g].tocsr()
+            A0 = sp.csr_matrix((A0.data, g2l[A0.indices], A0.indptr), shape=(self.n_owned, self.n_vertices))
+            assert (A0.indices >= 0).all()
+            P0 = levels[0]["P"][owned_g].tocsr()
+            R0 = levels[0]["R"][:, owned_g].tocsr()          # coarse rows x this rank's fine columns (local ids = 0..n_owned)
+            fine_ops = (A0, P0, R0, levels[0]["dinv"][owned_g], levels[0]["A"].diagonal()[owned_g],
+                        np.diff(levels[0]["A"].indptr)[owned_g] == 1)
+        self._ck(self.lib.fedmx_amg_reset(self.h))
         for l, lv in enumerate(levels):
             A = lv["A"]
             dinv = lv["dinv"].copy()
             isolated = np.diff(A.indptr) == 1            # Dirichlet rows: make the damped sweep exact
-            dinv[isolated] = 1.0 / (lv["omega"] * A.diagonal()[isolated])
+            diagA = A.diagonal()
+            if l == 0 and fine_ops is not None:
+                A, P, R, dinv, diagA, isolated = fine_ops
+                dinv = dinv.copy()
+            dinv[isolated] = 1.0 / (lv["omega"] * diagA[isolated])
             if "P" in lv:
-                P, R = lv["P"], lv["R"]
+                if not (l == 0 and fine_ops is not None):
+                    P, R = lv["P"], lv["R"]
                 arrs = [i32(A.indptr), i32(A.indices), f64(A.data), i32(P.indptr), i32(P.indices), f64(P.data),
                         i32(R.indptr), i32(R.indices), f64(R.data)]
                 self._ck(self.lib.fedmx_amg_add_level(self.h, A.shape[0], _np_ptr(f64(dinv)), float(lv["omega"]),

@@ -67,7 +67,7 @@ class StreamerCase:
             x_lap[:, :2] = np.log(1e13)
             x_lap[:, 2] = U_W * m.coords[:, 1] / BOX
             self.hot.jacobian(torch.from_numpy(x_lap.ravel()).to(self.hot.device), 5e-12, 1e30)
-            self.hot.setup_two_stage_preconditioner(2, self.bc_nodes)
+            self.hot.setup_two_stage_preconditioner(2, self.bc_nodes, local_mesh=self.local)
         elif precond != "bjacobi":
             raise ValueError("precond must be 'amg' or 'bjacobi'")
         self.newton_kw = dict(rtol=newton_rtol, max_it=newton_max_it, ksp_rtol=ksp_rtol, ksp_restart=ksp_restart,
@@ -120,7 +120,7 @@ class StreamerCase:
         phi = pot.new_vector()
         if self.precond == "amg":
             pot.jacobian(phi, 1.0, 1.0)
-            pot.setup_two_stage_preconditioner(0, self.bc_nodes)
+            pot.setup_two_stage_preconditioner(0, self.bc_nodes, local_mesh=self.local)
         if laplace_guess:
             phi.copy_(torch.from_numpy(U_W * m.coords[:, 1] / BOX))
         res = pot.newton(phi, 1.0, 1.0, rtol=1e-12, atol=0.0, max_it=5 if not laplace_guess else 1, ksp_rtol=ksp_rtol,
