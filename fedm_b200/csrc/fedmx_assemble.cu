@@ -16,6 +16,7 @@
 #include <math.h>
 
 #include "fedmx_internal.h"
+#include "quadrature_tables.h"
 
 namespace {
 
@@ -258,6 +259,114 @@ struct PoissonModel {
 };
 
 // =====================================================================================================
+// Time-of-flight model (N_eq = 1: ln n_e), drift-diffusion-reaction with constant D, w and an analytic source.
+// Reference: tests/integrated_tests/time_of_flight/fedm_tof.py:116-127 (u_analytical, Gamma = -grad(D e^u) + w e^u,
+// f declared degree=2 => FFC evaluates its P2 nodal interpolant: 3 vertices + 3 edge midpoints) over
+// fedm/functions.py:350-368.  Quadrature: no global degree is set, UFL estimates 8 => collapsed Gauss-Jacobi
+// m = 5, 25 points (pinned by the golden VTU).
+// params: [0]=D [1]=w_z [2]=alpha ;  mp.t = time of the new level ;  fields: [0]=BDF2 history
+// =====================================================================================================
+struct TofModel {
+    static constexpr int NEQ = 1;
+    static constexpr int NF = 1;
+
+    static __device__ __forceinline__ double source(const ModelParams &mp, double r, double z) {
+        const double D = mp.p[0], w = mp.p[1], al = mp.p[2], t = mp.t;
+        const double dz = z - w * t;
+        const double pi = 3.14159265358979323846;
+        return exp(-(dz * dz + r * r) / (4.0 * D * t) + al * w * t) * (w * al) / (8.0 * (pi * sqrt(pi)) * ((D * t) * sqrt(D * t)));
+    }
+
+    template <bool JAC>
+    static __device__ __forceinline__ void row(const ModelParams &mp, const Vtx<1, 1> &a, const Vtx<1, 1> &p,
+                                               const Vtx<1, 1> &n, uint32_t, uint32_t, RowOut<1> &o) {
+        const double e1r = p.r - a.r, e1z = p.z - a.z, e2r = n.r - a.r, e2z = n.z - a.z;
+        const double det = e1r * e2z - e1z * e2r;
+        const double inv = 1.0 / det;
+        const double gpr = e2z * inv, gpz = -e2r * inv;
+        const double gnr = -e1z * inv, gnz = e1r * inv;
+        const double gar = -gpr - gnr, gaz = -gpz - gnz;
+        const double gr[3] = {gar, gpr, gnr}, gz[3] = {gaz, gpz, gnz};
+        const double adet = fabs(det);
+        const double Hr = a.u[0] * gar + p.u[0] * gpr + n.u[0] * gnr;
+        const double Hz = a.u[0] * gaz + p.u[0] * gpz + n.u[0] * gnz;
+        const double D = mp.p[0], wz = mp.p[1];
+        const double tr = mp.dt / mp.dt_old;
+        const double ct = (1.0 + 2.0 * tr) / ((1.0 + tr) * mp.dt);
+        // P2 nodal values of the source: vertices (a,p,n) and midpoints opposite to a, p, n
+        const double fa = source(mp, a.r, a.z), fp = source(mp, p.r, p.z), fn = source(mp, n.r, n.z);
+        const double fma_ = source(mp, 0.5 * (p.r + n.r), 0.5 * (p.z + n.z));
+        const double fmp = source(mp, 0.5 * (a.r + n.r), 0.5 * (a.z + n.z));
+        const double fmn = source(mp, 0.5 * (a.r + p.r), 0.5 * (a.z + p.z));
+        // Gamma . g_a = e^u ( -D H + w ) . g_a
+        const double Pga = (-D * Hr) * gar + (-D * Hz + wz) * gaz;
+        double R = 0.0, J0 = 0.0, J1 = 0.0, J2 = 0.0;
+        for (int q = 0; q < 25; ++q) {
+            const double l0 = kTriGJ5[q][0], l1 = kTriGJ5[q][1], l2 = kTriGJ5[q][2];
+            const double W = kTriGJ5[q][3] * adet * kTwoPi * (l0 * a.r + l1 * p.r + l2 * n.r);
+            const double u = l0 * a.u[0] + l1 * p.u[0] + l2 * n.u[0];
+            const double h = l0 * a.f[0] + l1 * p.f[0] + l2 * n.f[0];
+            const double ne = exp(u);
+            const double beta = ct * u + h;
+            const double f = fa * l0 * (2.0 * l0 - 1.0) + fp * l1 * (2.0 * l1 - 1.0) + fn * l2 * (2.0 * l2 - 1.0) +
+                             4.0 * (fma_ * l1 * l2 + fmp * l0 * l2 + fmn * l0 * l1);
+            R += W * ((ne * beta - f) * l0 - ne * Pga);
+            if (JAC) {
+                const double c0 = W * ne * ((beta + ct) * l0 - Pga);     // multiplies lambda_b
+                const double c1 = W * ne * D;                             // multiplies g_b . g_a
+                J0 += c0 * l0 + c1 * (gr[0] * gar + gz[0] * gaz);
+                J1 += c0 * l1 + c1 * (gr[1] * gar + gz[1] * gaz);
+                J2 += c0 * l2 + c1 * (gr[2] * gar + gz[2] * gaz);
+            }
+        }
+        o.R[0] = R;
+        if (JAC) { o.J[0][0] = J0; o.J[1][0] = J1; o.J[2][0] = J2; }
+    }
+};
+
+// =====================================================================================================
+// L2 projection onto P1 (N_eq = 1): find x with (x, v) = (g, v), Cartesian measure, degree-4 (6-point) rule.
+// Reference: dolfin project(): n_num = project(exp(u_new), V) (fedm_tof.py:165) and the reduced field
+// project(1e21*sqrt(dot(-grad(Phi),-grad(Phi)))/N0) (fedm_gd.py:309, 432).  Written as the linear residual
+// R_a = sum_q w |detJ| (x - g) lambda_a so that the common Newton/GMRES path solves it in one iteration.
+// params: [0] = mode (0: g = exp(field0), 1: g = scale*|grad field0|)  [1] = scale ;  fields: [0] = P1 input
+// =====================================================================================================
+struct ProjectionModel {
+    static constexpr int NEQ = 1;
+    static constexpr int NF = 1;
+
+    template <bool JAC>
+    static __device__ __forceinline__ void row(const ModelParams &mp, const Vtx<1, 1> &a, const Vtx<1, 1> &p,
+                                               const Vtx<1, 1> &n, uint32_t, uint32_t, RowOut<1> &o) {
+        const double e1r = p.r - a.r, e1z = p.z - a.z, e2r = n.r - a.r, e2z = n.z - a.z;
+        const double det = e1r * e2z - e1z * e2r;
+        const double adet = fabs(det);
+        const int mode = int(mp.p[0]);
+        double gconst = 0.0;
+        if (mode == 1) {
+            const double inv = 1.0 / det;
+            const double gpr = e2z * inv, gpz = -e2r * inv, gnr = -e1z * inv, gnz = e1r * inv;
+            const double gar = -gpr - gnr, gaz = -gpz - gnz;
+            const double Gr = a.f[0] * gar + p.f[0] * gpr + n.f[0] * gnr;
+            const double Gz = a.f[0] * gaz + p.f[0] * gpz + n.f[0] * gnz;
+            gconst = mp.p[1] * sqrt(Gr * Gr + Gz * Gz);
+        }
+        double R = 0.0, J0 = 0.0, J1 = 0.0, J2 = 0.0;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+            const double l0 = kTriDeg4[q][0], l1 = kTriDeg4[q][1], l2 = kTriDeg4[q][2];
+            const double W = kTriDeg4[q][3] * adet;
+            const double x = l0 * a.u[0] + l1 * p.u[0] + l2 * n.u[0];
+            const double g = mode == 1 ? gconst : exp(l0 * a.f[0] + l1 * p.f[0] + l2 * n.f[0]);
+            R += W * (x - g) * l0;
+            if (JAC) { J0 += W * l0 * l0; J1 += W * l0 * l1; J2 += W * l0 * l2; }
+        }
+        o.R[0] = R;
+        if (JAC) { o.J[0][0] = J0; o.J[1][0] = J1; o.J[2][0] = J2; }
+    }
+};
+
+// =====================================================================================================
 // Generic row kernel
 // =====================================================================================================
 template <int NB>
@@ -402,6 +511,10 @@ int assemble_dispatch(fedmx_ctx *ctx, const double *d_x, double dt, double dt_ol
             return launch_assembly<StreamerModel>(ctx, d_x, d_b, jac);
         case FEDMX_MODEL_POISSON:
             return launch_assembly<PoissonModel>(ctx, d_x, d_b, jac);
+        case FEDMX_MODEL_TOF:
+            return launch_assembly<TofModel>(ctx, d_x, d_b, jac);
+        case FEDMX_MODEL_PROJECTION:
+            return launch_assembly<ProjectionModel>(ctx, d_x, d_b, jac);
         default:
             ctx->err = "assemble: model not implemented";
             return FEDMX_EUNSUPPORTED;
@@ -422,6 +535,8 @@ extern "C" int fedmx_model_set(fedmx_ctx *ctx, int model_id, int n_params, const
     switch (model_id) {
         case FEDMX_MODEL_STREAMER: neq = StreamerModel::NEQ; nf = StreamerModel::NF; break;
         case FEDMX_MODEL_POISSON: neq = PoissonModel::NEQ; nf = PoissonModel::NF; break;
+        case FEDMX_MODEL_TOF: neq = TofModel::NEQ; nf = TofModel::NF; break;
+        case FEDMX_MODEL_PROJECTION: neq = ProjectionModel::NEQ; nf = ProjectionModel::NF; break;
         default:
             ctx->err = "fedmx_model_set: unknown model id";
             return FEDMX_EUNSUPPORTED;

@@ -12,7 +12,7 @@ import torch
 
 from . import lib as _l
 
-MODEL_STREAMER, MODEL_TOF, MODEL_GLOW, MODEL_POISSON = 1, 2, 3, 4
+MODEL_STREAMER, MODEL_TOF, MODEL_GLOW, MODEL_POISSON, MODEL_PROJECTION = 1, 2, 3, 4, 5
 
 SNES_REASONS = {2: "CONVERGED_FNORM_ABS", 3: "CONVERGED_FNORM_RELATIVE", 4: "CONVERGED_SNORM_RELATIVE",
                 -3: "DIVERGED_LINEAR_SOLVE", -4: "DIVERGED_FNORM_NAN", -5: "DIVERGED_MAX_IT"}

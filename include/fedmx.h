@@ -40,7 +40,8 @@ enum {
     FEDMX_MODEL_STREAMER = 1,   /* tests/integrated_tests/streamer_discharge/fedm_streamer.py:243-279 */
     FEDMX_MODEL_TOF = 2,        /* tests/integrated_tests/time_of_flight/fedm_tof.py:120-127 */
     FEDMX_MODEL_GLOW = 3,       /* tests/integrated_tests/glow_discharge/fedm_gd.py:349-385 */
-    FEDMX_MODEL_POISSON = 4     /* weak_form_Poisson_equation alone (initial potential), fedm_streamer.py:210-223 */
+    FEDMX_MODEL_POISSON = 4,    /* weak_form_Poisson_equation alone (initial potential), fedm_streamer.py:210-223 */
+    FEDMX_MODEL_PROJECTION = 5  /* dolfin project() onto P1: fedm_tof.py:165, fedm_gd.py:309,432 */
 };
 
 /* SNES convergence reasons (subset of PETSc's SNESConvergedReason the reference can observe) */

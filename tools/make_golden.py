@@ -55,6 +55,12 @@ def main():
             assert out["topology"].min() == 0 and out["topology"].max() == NV - 1
             assert sorted(set(out["cell_dofs"].tolist())) == list(range(NV))
     np.savez_compressed(OUT / "glow_h5.npz", **out)
+    # --- input decks of the glow and streamer cases (plain data files read by the reference's fedm/file_io.py)
+    for case in ("glow_discharge", "streamer_discharge"):
+        dst = OUT / f"{case}_input"
+        if dst.exists():
+            shutil.rmtree(dst)
+        shutil.copytree(REF / case / "file_input", dst)
     for k, v in out.items():
         print(k, v.shape, v.dtype, float(np.min(v)), float(np.max(v)))
 
