@@ -40,6 +40,7 @@ struct AsmArgs {
 // One vertex as seen by a model: coordinates, unknowns, coefficient fields.
 template <int NEQ, int NF>
 struct Vtx {
+    int32_t id;             // local vertex index (FFC orients non-symmetric quadrature rules by ascending index)
     double r, z;
     double u[NEQ];
     double f[NF > 0 ? NF : 1];
@@ -48,6 +49,7 @@ struct Vtx {
 template <int NEQ, int NF>
 __device__ __forceinline__ void load_vertex(const AsmArgs &A, int32_t v, Vtx<NEQ, NF> &o) {
     const double2 c = *reinterpret_cast<const double2 *>(A.coords + 2 * int64_t(v));
+    o.id = v;
     o.r = c.x;
     o.z = c.y;
 #pragma unroll
@@ -300,9 +302,12 @@ struct TofModel {
         const double fmn = source(mp, 0.5 * (a.r + p.r), 0.5 * (a.z + p.z));
         // Gamma . g_a = e^u ( -D H + w ) . g_a
         const double Pga = (-D * Hr) * gar + (-D * Hz + wz) * gaz;
+        // The collapsed rule is not symmetric: FFC places it on the reference cell whose vertices are the cell's
+        // vertices in ascending index order, so map (a,p,n) to their ranks in that order.
+        const int ra = (a.id > p.id) + (a.id > n.id), rp = (p.id > a.id) + (p.id > n.id), rn = 3 - ra - rp;
         double R = 0.0, J0 = 0.0, J1 = 0.0, J2 = 0.0;
         for (int q = 0; q < 25; ++q) {
-            const double l0 = kTriGJ5[q][0], l1 = kTriGJ5[q][1], l2 = kTriGJ5[q][2];
+            const double l0 = kTriGJ5[q][ra], l1 = kTriGJ5[q][rp], l2 = kTriGJ5[q][rn];
             const double W = kTriGJ5[q][3] * adet * kTwoPi * (l0 * a.r + l1 * p.r + l2 * n.r);
             const double u = l0 * a.u[0] + l1 * p.u[0] + l2 * n.u[0];
             const double h = l0 * a.f[0] + l1 * p.f[0] + l2 * n.f[0];
