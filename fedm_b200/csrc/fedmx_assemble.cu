@@ -371,6 +371,8 @@ struct ProjectionModel {
     }
 };
 
+#include "glow_model.cuh"
+
 // =====================================================================================================
 // Generic row kernel
 // =====================================================================================================
@@ -518,6 +520,8 @@ int assemble_dispatch(fedmx_ctx *ctx, const double *d_x, double dt, double dt_ol
             return launch_assembly<PoissonModel>(ctx, d_x, d_b, jac);
         case FEDMX_MODEL_TOF:
             return launch_assembly<TofModel>(ctx, d_x, d_b, jac);
+        case FEDMX_MODEL_GLOW:
+            return launch_assembly<GlowModel>(ctx, d_x, d_b, jac);
         case FEDMX_MODEL_PROJECTION:
             return launch_assembly<ProjectionModel>(ctx, d_x, d_b, jac);
         default:
@@ -541,6 +545,7 @@ extern "C" int fedmx_model_set(fedmx_ctx *ctx, int model_id, int n_params, const
         case FEDMX_MODEL_STREAMER: neq = StreamerModel::NEQ; nf = StreamerModel::NF; break;
         case FEDMX_MODEL_POISSON: neq = PoissonModel::NEQ; nf = PoissonModel::NF; break;
         case FEDMX_MODEL_TOF: neq = TofModel::NEQ; nf = TofModel::NF; break;
+        case FEDMX_MODEL_GLOW: neq = GlowModel::NEQ; nf = GlowModel::NF; break;
         case FEDMX_MODEL_PROJECTION: neq = ProjectionModel::NEQ; nf = ProjectionModel::NF; break;
         default:
             ctx->err = "fedmx_model_set: unknown model id";

@@ -8,7 +8,7 @@
 #include "../../include/fedmx.h"
 
 #define FEDMX_MAX_EQ 5
-#define FEDMX_MAX_PARAMS 64
+#define FEDMX_MAX_PARAMS 128
 #define FEDMX_MAX_BC 16
 #define FEDMX_SLICE 32
 

@@ -304,6 +304,20 @@ __global__ void strided_copy_kernel(const double *__restrict__ src, int64_t ss, 
         dst[i * ds + dof] = src[i * ss + so];
 }
 
+// dst = src * mul / div (strided); the reference's ESR rule D = kB*Tgas*mu/e (fedm/functions.py:633)
+__global__ void strided_scale_kernel(const double *__restrict__ src, int64_t ss, int64_t so, double *__restrict__ dst,
+                                     int64_t ds, int64_t dof, int64_t n, double mul, double div) {
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
+        dst[i * ds + dof] = __ddiv_rn(__dmul_rn(mul, src[i * ss + so]), div);
+}
+
+// dst = exp(x[.,ca] - x[.,cb]) : mean energy from ln w_e - ln n_e (fedm_gd.py:452)
+__global__ void exp_diff_kernel(const double *__restrict__ x, int n_eq, int ca, int cb, double *__restrict__ dst,
+                                int64_t ds, int64_t dof, int64_t n) {
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
+        dst[i * ds + dof] = exp(x[i * n_eq + ca] - x[i * n_eq + cb]);
+}
+
 inline unsigned grid_for(int64_t n, int threads, int cap = kMaxRedBlocks) {
     int64_t b = (n + threads - 1) / threads;
     if (b < 1) b = 1;
@@ -512,6 +526,28 @@ extern "C" int fedmx_strided_copy(fedmx_ctx *ctx, const double *d_src, int64_t s
     FEDMX_REQUIRE(ctx, d_src && d_dst && n >= 0, "fedmx_strided_copy: null argument");
     if (n == 0) return FEDMX_OK;
     strided_copy_kernel<<<grid_for(n, 256, 4736), 256, 0, ctx->stream>>>(d_src, src_stride, src_off, d_dst, dst_stride, dst_off, n);
+    ctx->launches++;
+    FEDMX_CHECK_CUDA(ctx, cudaGetLastError());
+    return FEDMX_OK;
+}
+
+extern "C" int fedmx_strided_scale(fedmx_ctx *ctx, const double *d_src, int64_t src_stride, int64_t src_off, double *d_dst,
+                                   int64_t dst_stride, int64_t dst_off, int64_t n, double mul, double div) {
+    if (!ctx) return FEDMX_EINVAL;
+    FEDMX_REQUIRE(ctx, d_src && d_dst && n >= 0, "fedmx_strided_scale: null argument");
+    if (n == 0) return FEDMX_OK;
+    strided_scale_kernel<<<grid_for(n, 256, 4736), 256, 0, ctx->stream>>>(d_src, src_stride, src_off, d_dst, dst_stride, dst_off, n, mul, div);
+    ctx->launches++;
+    FEDMX_CHECK_CUDA(ctx, cudaGetLastError());
+    return FEDMX_OK;
+}
+
+extern "C" int fedmx_exp_diff(fedmx_ctx *ctx, const double *d_x, int n_eq, int comp_a, int comp_b, double *d_dst,
+                              int64_t dst_stride, int64_t dst_off, int64_t n) {
+    if (!ctx) return FEDMX_EINVAL;
+    FEDMX_REQUIRE(ctx, d_x && d_dst && n >= 0 && comp_a >= 0 && comp_b >= 0 && comp_a < n_eq && comp_b < n_eq, "fedmx_exp_diff: bad arguments");
+    if (n == 0) return FEDMX_OK;
+    exp_diff_kernel<<<grid_for(n, 256, 4736), 256, 0, ctx->stream>>>(d_x, n_eq, comp_a, comp_b, d_dst, dst_stride, dst_off, n);
     ctx->launches++;
     FEDMX_CHECK_CUDA(ctx, cudaGetLastError());
     return FEDMX_OK;

@@ -256,6 +256,12 @@ class HotPath:
     def strided_copy(self, src, src_stride, src_off, dst, dst_stride, dst_off, n):
         self._ck(self.lib.fedmx_strided_copy(self.h, _ptr(src), src_stride, src_off, _ptr(dst), dst_stride, dst_off, n))
 
+    def strided_scale(self, src, src_stride, src_off, dst, dst_stride, dst_off, n, mul, div=1.0):
+        self._ck(self.lib.fedmx_strided_scale(self.h, _ptr(src), src_stride, src_off, _ptr(dst), dst_stride, dst_off, n, mul, div))
+
+    def exp_diff(self, x, n_eq, comp_a, comp_b, dst, dst_stride, dst_off, n):
+        self._ck(self.lib.fedmx_exp_diff(self.h, _ptr(x), n_eq, comp_a, comp_b, _ptr(dst), dst_stride, dst_off, n))
+
     def launch_count(self, reset=False):
         return int(self.lib.fedmx_launch_count(self.h, 1 if reset else 0))
 

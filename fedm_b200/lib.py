@@ -57,6 +57,10 @@ SIGNATURES = {
                                      C.c_double, C.c_void_p, C.c_int64]),
     "fedmx_strided_copy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
                                      C.c_int64, C.c_int64]),
+    "fedmx_strided_scale": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
+                                      C.c_int64, C.c_int64, C.c_double, C.c_double]),
+    "fedmx_exp_diff": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int64,
+                                 C.c_int64]),
     "fedmx_comm_unique_id": (C.c_int, [C.c_char_p]),
     "fedmx_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char_p]),
     "fedmx_halo_set": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -179,6 +179,15 @@ int fedmx_interp_table(fedmx_ctx *ctx, const double *d_x, int64_t x_stride, int6
 int fedmx_strided_copy(fedmx_ctx *ctx, const double *d_src, int64_t src_stride, int64_t src_off,
                        double *d_dst, int64_t dst_stride, int64_t dst_off, int64_t n);
 
+/* dst[i*dst_stride+dst_off] = mul * src[i*src_stride+src_off] / div : the 'ESR' rule D = kB*Tgas*mu/e
+ * (fedm/functions.py:633) and other per-node scalings, same operation order as the reference. */
+int fedmx_strided_scale(fedmx_ctx *ctx, const double *d_src, int64_t src_stride, int64_t src_off,
+                        double *d_dst, int64_t dst_stride, int64_t dst_off, int64_t n, double mul, double div);
+/* dst[i*dst_stride+dst_off] = exp(x[i*n_eq+comp_a] - x[i*n_eq+comp_b]) : mean electron energy from ln w_e and ln n_e
+ * (fedm_gd.py:452). */
+int fedmx_exp_diff(fedmx_ctx *ctx, const double *d_x, int n_eq, int comp_a, int comp_b,
+                   double *d_dst, int64_t dst_stride, int64_t dst_off, int64_t n);
+
 /* ---- multi-GPU (north_star (f): mesh partition, halo exchange, allreduce over NCCL) ---------------- */
 /* The host creates the id on rank 0 (fedmx_comm_unique_id), broadcasts the 128 bytes with its own
  * plumbing (torch.distributed) and every rank calls fedmx_comm_init.  Replaces MPI inside dolfin/PETSc. */
