@@ -14,6 +14,7 @@
 // rows, so every store instruction writes 256 contiguous bytes.
 // Dirichlet rows are fused into the epilogue: b_i = x_i - g, Jacobian row = unit row (pattern kept).
 #include <math.h>
+#include <stdlib.h>
 
 #include "fedmx_internal.h"
 #include "quadrature_tables.h"
@@ -76,8 +77,39 @@ struct RowOut {
 // fields: [0]=hist_i [1]=hist_e  (BDF2 history, fedmx_bdf2_history)
 // =====================================================================================================
 struct StreamerModel {
+    static constexpr int MINB = 3, MINB_RES = 4;
     static constexpr int NEQ = 3;
     static constexpr int NF = 2;
+
+    // facet (a,b): b is local vertex LB (1 = p, 2 = n), c the opposite vertex
+    template <bool JAC, int LB>
+    static __device__ __forceinline__ void facet(const Vtx<3, 2> &a, const Vtx<3, 2> &b, const Vtx<3, 2> &c, const double *gr,
+                                                 const double *gz, double Gr, double Gz, double iEm, double mu, double dmu,
+                                                 RowOut<3> &o) {
+        const double tr_ = b.r - a.r, tz_ = b.z - a.z;
+        const double L = sqrt(tr_ * tr_ + tz_ * tz_);
+        double nr = tz_ / L, nz = -tr_ / L;
+        if (nr * (c.r - a.r) + nz * (c.z - a.z) > 0.0) { nr = -nr; nz = -nz; }
+        const double Gn = Gr * nr + Gz * nz;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const double t = kGL2_t[q];
+            const double la = 1.0 - t;
+            const double rq = la * a.r + t * b.r;
+            const double ne = exp(la * a.u[1] + t * b.u[1]);
+            const double W = 0.5 * L * kTwoPi * rq * ne * la;     // weight * n_e * test function
+            o.R[1] += W * mu * Gn;
+            if (JAC) {
+                o.J[0][4] += W * mu * Gn * la;
+                o.J[LB][4] += W * mu * Gn * t;
+#pragma unroll
+                for (int bb = 0; bb < 3; ++bb) {
+                    const double Ghb = (Gr * gr[bb] + Gz * gz[bb]) * iEm;
+                    o.J[bb][5] += W * (dmu * Ghb * Gn + mu * (gr[bb] * nr + gz[bb] * nz));
+                }
+            }
+        }
+    }
 
     template <bool JAC>
     static __device__ __forceinline__ void row(const ModelParams &mp, const Vtx<3, 2> &a, const Vtx<3, 2> &p,
@@ -184,37 +216,10 @@ struct StreamerModel {
         }
         // --- exterior facets (a,p) and (a,n): 'Neumann' drift flux  2 pi r (-mu)(E.n) n_e v,  E = -G
         const uint32_t mask = uint32_t(mp.p[9]);
-#pragma unroll
-        for (int side = 0; side < 2; ++side) {
-            const uint32_t mk = side == 0 ? mk_ap : mk_an;
-            if (mk == 0 || !((mask >> mk) & 1u)) continue;
-            const Vtx<3, 2> &b = side == 0 ? p : n;        // other facet vertex
-            const Vtx<3, 2> &c = side == 0 ? n : p;        // opposite vertex
-            const int lb = side == 0 ? 1 : 2;
-            double tr_ = b.r - a.r, tz_ = b.z - a.z;
-            const double L = sqrt(tr_ * tr_ + tz_ * tz_);
-            double nr = tz_ / L, nz = -tr_ / L;
-            if (nr * (c.r - a.r) + nz * (c.z - a.z) > 0.0) { nr = -nr; nz = -nz; }
-            const double Gn = Gr * nr + Gz * nz;
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const double t = kGL2_t[q];
-                const double la = 1.0 - t;
-                const double rq = la * a.r + t * b.r;
-                const double ne = exp(la * a.u[1] + t * b.u[1]);
-                const double W = 0.5 * L * kTwoPi * rq * ne * la;     // weight * n_e * test function
-                o.R[1] += W * mu * Gn;
-                if (JAC) {
-                    o.J[0][4] += W * mu * Gn * la;
-                    o.J[lb][4] += W * mu * Gn * t;
-#pragma unroll
-                    for (int bb = 0; bb < 3; ++bb) {
-                        const double Ghb = (Gr * gr[bb] + Gz * gz[bb]) * iEm;
-                        o.J[bb][5] += W * (dmu * Ghb * Gn + mu * (gr[bb] * nr + gz[bb] * nz));
-                    }
-                }
-            }
-        }
+        if (mk_ap != 0 && ((mask >> mk_ap) & 1u))
+            facet<JAC, 1>(a, p, n, gr, gz, Gr, Gz, iEm, mu, dmu, o);
+        if (mk_an != 0 && ((mask >> mk_an) & 1u))
+            facet<JAC, 2>(a, n, p, gr, gz, Gr, Gz, iEm, mu, dmu, o);
     }
 };
 
@@ -224,6 +229,7 @@ struct StreamerModel {
 // initial potential, fedm_streamer.py:210-223.  params: [0] = kappa = e/eps0.  Degree-2 quadrature.
 // =====================================================================================================
 struct PoissonModel {
+    static constexpr int MINB = 2, MINB_RES = 2;
     static constexpr int NEQ = 1;
     static constexpr int NF = 2;
 
@@ -269,6 +275,7 @@ struct PoissonModel {
 // params: [0]=D [1]=w_z [2]=alpha ;  mp.t = time of the new level ;  fields: [0]=BDF2 history
 // =====================================================================================================
 struct TofModel {
+    static constexpr int MINB = 2, MINB_RES = 2;
     static constexpr int NEQ = 1;
     static constexpr int NF = 1;
 
@@ -337,6 +344,7 @@ struct TofModel {
 // params: [0] = mode (0: g = exp(field0), 1: g = scale*|grad field0|)  [1] = scale ;  fields: [0] = P1 input
 // =====================================================================================================
 struct ProjectionModel {
+    static constexpr int MINB = 2, MINB_RES = 2;
     static constexpr int NEQ = 1;
     static constexpr int NF = 1;
 
@@ -390,8 +398,19 @@ __device__ __forceinline__ void add_block(double *val, int64_t group_base, int s
     for (int e = 0; e < NB; ++e) dst[e * FEDMX_SLICE] += blk[e];
 }
 
-template <class Model, bool JAC>
-__global__ void __launch_bounds__(128) assemble_rows_kernel(AsmArgs A) {
+// Zero block row `comp` with static register indices (comp is a run-time value: a dynamic index would push the
+// accumulators into local memory).
+template <int NEQ>
+__device__ __forceinline__ void zero_row(double *blk, int comp) {
+#pragma unroll
+    for (int k = 0; k < NEQ; ++k)
+#pragma unroll
+        for (int l = 0; l < NEQ; ++l)
+            if (k == comp) blk[k * NEQ + l] = 0.0;
+}
+
+template <class Model, bool JAC, int MINB>
+__global__ void __launch_bounds__(128, MINB) assemble_rows_kernel(AsmArgs A) {
     constexpr int NEQ = Model::NEQ, NF = Model::NF, NB = NEQ * NEQ;
     const int64_t row = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     const int64_t s = row / FEDMX_SLICE;
@@ -437,19 +456,13 @@ __global__ void __launch_bounds__(128) assemble_rows_kernel(AsmArgs A) {
             }
 #pragma unroll
             for (int q = 0; q < NB; ++q) carry[q] += o.J[1][q];
-            if (bc) {
-#pragma unroll
-                for (int l = 0; l < NEQ; ++l) carry[bc_comp * NEQ + l] = 0.0;
-            }
+            if (bc) zero_row<NEQ>(carry, bc_comp);
             // block (i, vp) is complete (or the partial first block of a closed fan): write it
             store_block<NB>(A.val, gbase, PACK_SLOT_P(pack), lane, carry);
 #pragma unroll
             for (int q = 0; q < NB; ++q) carry[q] = o.J[2][q];
             if (PACK_LAST(pack)) {
-                if (bc) {
-#pragma unroll
-                    for (int l = 0; l < NEQ; ++l) carry[bc_comp * NEQ + l] = 0.0;
-                }
+                if (bc) zero_row<NEQ>(carry, bc_comp);
                 if (PACK_CLOSED(pack)) add_block<NB>(A.val, gbase, PACK_SLOT_N(pack), lane, carry);
                 else store_block<NB>(A.val, gbase, PACK_SLOT_N(pack), lane, carry);
             }
@@ -457,10 +470,15 @@ __global__ void __launch_bounds__(128) assemble_rows_kernel(AsmArgs A) {
     }
     if (!active) return;
     if (bc) {
-        R[bc_comp] = va.u[bc_comp] - A.mp.bc_values[bc - 1];
-        if (JAC) {
+        const double g = A.mp.bc_values[bc - 1];
 #pragma unroll
-            for (int l = 0; l < NEQ; ++l) diag[bc_comp * NEQ + l] = (l == bc_comp) ? 1.0 : 0.0;
+        for (int k = 0; k < NEQ; ++k)
+            if (k == bc_comp) R[k] = va.u[k] - g;
+        if (JAC) {
+            zero_row<NEQ>(diag, bc_comp);
+#pragma unroll
+            for (int k = 0; k < NEQ; ++k)
+                if (k == bc_comp) diag[k * NEQ + k] = 1.0;
         }
     }
     if (JAC) store_block<NB>(A.val, gbase, diag_slot, lane, diag);
@@ -494,8 +512,20 @@ int launch_assembly(fedmx_ctx *ctx, const double *d_x, double *d_b, bool jac) {
     const int64_t rows = ctx->sell.n_slices * FEDMX_SLICE;
     const unsigned blocks = unsigned((rows + threads - 1) / threads);
     ProfScope prof(ctx, jac ? FEDMX_PROF_ASM_JAC : FEDMX_PROF_ASM_RES);
-    if (jac) assemble_rows_kernel<Model, true><<<blocks, threads, 0, ctx->stream>>>(A);
-    else assemble_rows_kernel<Model, false><<<blocks, threads, 0, ctx->stream>>>(A);
+    // resident CTAs per SM the kernel is compiled for (register cap 65536/(128*MINB)); FEDMX_ASM_MINB overrides for tuning
+    static const int env_minb = getenv("FEDMX_ASM_MINB") ? atoi(getenv("FEDMX_ASM_MINB")) : 0;
+    // measured on B200 at 10 M DOF (tools/bench_assembly.py): Jacobian 1.48/1.22/1.49 ms and residual 1.02/0.86/0.77 ms
+    // for 2/3/4 resident CTAs per SM
+    const int minb = env_minb ? env_minb : (jac ? Model::MINB : Model::MINB_RES);
+    if (jac) {
+        if (minb >= 4) assemble_rows_kernel<Model, true, 4><<<blocks, threads, 0, ctx->stream>>>(A);
+        else if (minb == 3) assemble_rows_kernel<Model, true, 3><<<blocks, threads, 0, ctx->stream>>>(A);
+        else assemble_rows_kernel<Model, true, 2><<<blocks, threads, 0, ctx->stream>>>(A);
+    } else {
+        if (minb >= 4) assemble_rows_kernel<Model, false, 4><<<blocks, threads, 0, ctx->stream>>>(A);
+        else if (minb == 3) assemble_rows_kernel<Model, false, 3><<<blocks, threads, 0, ctx->stream>>>(A);
+        else assemble_rows_kernel<Model, false, 2><<<blocks, threads, 0, ctx->stream>>>(A);
+    }
     ctx->launches++;
     FEDMX_CHECK_CUDA(ctx, cudaGetLastError());
     return FEDMX_OK;

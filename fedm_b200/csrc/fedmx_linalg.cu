@@ -14,7 +14,7 @@
 namespace {
 
 constexpr int kRedThreads = 256;
-constexpr int kMaxRedBlocks = 1184;   // 148 SMs x 8
+constexpr int kMaxRedBlocks = 2368;   // 148 SMs x 16
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -154,36 +154,51 @@ __global__ void apply_dinv_kernel(SellView S, const double *__restrict__ dinv, c
 }
 
 // ---- reductions --------------------------------------------------------------------------------------------
-// partial[j*gridDim.x + blockIdx.x] = sum over this block's grid-stride chunk of V_j . w   (j < nvec)
-// and partial[nvec*gridDim.x + blockIdx.x] = w . w
-template <int JT>
-__global__ void __launch_bounds__(kRedThreads) multidot_kernel(const double *__restrict__ V, int64_t ld, int nvec,
+// Fused multi-dot of classical Gram-Schmidt: partial[(j0+j)*gridDim.x + blockIdx.x] = chunk of V_{j0+j} . w for j < J
+// (J compile-time, so that the J+1 load streams of an iteration are independent and stay in flight together), and,
+// if WW, partial[ww_slot*gridDim.x + blockIdx.x] = chunk of w . w.  Four elements per thread per iteration.
+template <int J, bool WW>
+__global__ void __launch_bounds__(kRedThreads) multidot_kernel(const double *__restrict__ V, int64_t ld, int j0, int ww_slot,
                                                                const double *__restrict__ w, int64_t n,
-                                                               double *__restrict__ partial, int with_ww) {
+                                                               double *__restrict__ partial) {
     __shared__ double smem[32];
-    for (int j0 = 0; j0 < nvec || (j0 == 0 && with_ww); j0 += JT) {
-        double acc[JT], ww = 0.0;
+    double acc[J > 0 ? J : 1], ww = 0.0;
 #pragma unroll
-        for (int j = 0; j < JT; ++j) acc[j] = 0.0;
-        for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
-            const double wi = w[i];
-            if (j0 == 0) ww = fma(wi, wi, ww);
+    for (int j = 0; j < J; ++j) acc[j] = 0.0;
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n; i += 4 * stride) {
+        double wv[4];
 #pragma unroll
-            for (int j = 0; j < JT; ++j)
-                if (j0 + j < nvec) acc[j] = fma(V[int64_t(j0 + j) * ld + i], wi, acc[j]);
-        }
+        for (int u = 0; u < 4; ++u) wv[u] = __ldcs(w + i + u * stride);
 #pragma unroll
-        for (int j = 0; j < JT; ++j) {
-            if (j0 + j < nvec) {
-                const double r = block_sum(acc[j], smem);
-                if (threadIdx.x == 0) partial[int64_t(j0 + j) * gridDim.x + blockIdx.x] = r;
-            }
+        for (int j = 0; j < J; ++j) {
+            const double *vj = V + int64_t(j0 + j) * ld + i;
+            double vv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) vv[u] = __ldcs(vj + u * stride);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc[j] = fma(vv[u], wv[u], acc[j]);
         }
-        if (j0 == 0 && with_ww) {
-            const double r = block_sum(ww, smem);
-            if (threadIdx.x == 0) partial[int64_t(nvec) * gridDim.x + blockIdx.x] = r;
+        if (WW) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) ww = fma(wv[u], wv[u], ww);
         }
-        if (nvec == 0) break;
+    }
+    for (; i < n; i += stride) {
+        const double wi = w[i];
+#pragma unroll
+        for (int j = 0; j < J; ++j) acc[j] = fma(V[int64_t(j0 + j) * ld + i], wi, acc[j]);
+        if (WW) ww = fma(wi, wi, ww);
+    }
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        const double r = block_sum(acc[j], smem);
+        if (threadIdx.x == 0) partial[int64_t(j0 + j) * gridDim.x + blockIdx.x] = r;
+    }
+    if (WW) {
+        const double r = block_sum(ww, smem);
+        if (threadIdx.x == 0) partial[int64_t(ww_slot) * gridDim.x + blockIdx.x] = r;
     }
 }
 
@@ -198,23 +213,41 @@ __global__ void __launch_bounds__(kRedThreads) finish_reduce_kernel(const double
     if (threadIdx.x == 0) out[j] = r;
 }
 
-// w -= sum_j h[j] V_j ; partial[blockIdx] = ||w_new||^2 chunk
-__global__ void __launch_bounds__(kRedThreads) multiaxpy_norm_kernel(const double *__restrict__ V, int64_t ld, int nvec,
-                                                                     const double *__restrict__ h, double *__restrict__ w,
-                                                                     int64_t n, double *__restrict__ partial) {
+// w -= sum_{j<J} h[j0+j] V_{j0+j} ; if NORM: partial[blockIdx] = chunk of ||w_new||^2
+template <int J, bool NORM>
+__global__ void __launch_bounds__(kRedThreads) multiaxpy_kernel(const double *__restrict__ V, int64_t ld, int j0,
+                                                                const double *__restrict__ h, double *__restrict__ w,
+                                                                int64_t n, double *__restrict__ partial) {
     __shared__ double smem[32];
-    __shared__ double hs[64];
-    if (threadIdx.x < nvec) hs[threadIdx.x] = h[threadIdx.x];
-    __syncthreads();
+    double hs[J];
+#pragma unroll
+    for (int j = 0; j < J; ++j) hs[j] = h[j0 + j];
     double ww = 0.0;
-    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
-        double wi = w[i];
-        for (int j = 0; j < nvec; ++j) wi = fma(-hs[j], V[int64_t(j) * ld + i], wi);
-        w[i] = wi;
-        ww = fma(wi, wi, ww);
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    for (; i + stride < n; i += 2 * stride) {
+        double w0 = w[i], w1 = w[i + stride];
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            const double *vj = V + int64_t(j0 + j) * ld + i;
+            w0 = fma(-hs[j], __ldcs(vj), w0);
+            w1 = fma(-hs[j], __ldcs(vj + stride), w1);
+        }
+        w[i] = w0;
+        w[i + stride] = w1;
+        if (NORM) ww = fma(w0, w0, fma(w1, w1, ww));
     }
-    const double r = block_sum(ww, smem);
-    if (threadIdx.x == 0) partial[blockIdx.x] = r;
+    for (; i < n; i += stride) {
+        double wi = w[i];
+#pragma unroll
+        for (int j = 0; j < J; ++j) wi = fma(-hs[j], V[int64_t(j0 + j) * ld + i], wi);
+        w[i] = wi;
+        if (NORM) ww = fma(wi, wi, ww);
+    }
+    if (NORM) {
+        const double r = block_sum(ww, smem);
+        if (threadIdx.x == 0) partial[blockIdx.x] = r;
+    }
 }
 
 // y = alpha * x  (alpha read from device memory as 1/ *inv_of if inv_of != null)
@@ -403,23 +436,60 @@ int fedmx_apply_dinv(fedmx_ctx *ctx, const double *d_r, double *d_z) {
     return FEDMX_OK;
 }
 
+template <bool WW>
+static void launch_multidot(fedmx_ctx *ctx, int J, unsigned blocks, const double *V, int64_t ld, int j0, int ww_slot,
+                            const double *w, int64_t n) {
+#define MD_CASE(JJ) case JJ: multidot_kernel<JJ, WW><<<blocks, kRedThreads, 0, ctx->stream>>>(V, ld, j0, ww_slot, w, n, ctx->d_red); break;
+    switch (J) {
+        MD_CASE(0) MD_CASE(1) MD_CASE(2) MD_CASE(3) MD_CASE(4) MD_CASE(5) MD_CASE(6) MD_CASE(7) MD_CASE(8)
+    }
+#undef MD_CASE
+    ctx->launches++;
+}
+
 // out_dev[0..nvec) = V_j . w (owned entries), out_dev[nvec] = w.w ; result stays on the device.
 int fedmx_multidot(fedmx_ctx *ctx, const double *V, int64_t ld, int nvec, const double *w, int64_t n, double *out_dev,
                    bool with_ww) {
-    const unsigned blocks = grid_for(n, kRedThreads);
-    multidot_kernel<8><<<blocks, kRedThreads, 0, ctx->stream>>>(V, ld, nvec, w, n, ctx->d_red, with_ww ? 1 : 0);
+    const unsigned blocks = grid_for(n, kRedThreads * 4);
+    int j0 = 0;
+    bool ww_done = !with_ww;
+    do {
+        const int J = nvec - j0 > 8 ? 8 : nvec - j0;
+        if (!ww_done) launch_multidot<true>(ctx, J, blocks, V, ld, j0, nvec, w, n);
+        else launch_multidot<false>(ctx, J, blocks, V, ld, j0, nvec, w, n);
+        ww_done = true;
+        j0 += J;
+    } while (j0 < nvec);
     finish_reduce_kernel<<<nvec + (with_ww ? 1 : 0), kRedThreads, 0, ctx->stream>>>(ctx->d_red, int(blocks), out_dev);
-    ctx->launches += 2;
+    ctx->launches++;
     FEDMX_CHECK_CUDA(ctx, cudaGetLastError());
     return FEDMX_OK;
 }
 
+template <bool NORM>
+static void launch_multiaxpy(fedmx_ctx *ctx, int J, unsigned blocks, const double *V, int64_t ld, int j0, const double *h,
+                             double *w, int64_t n) {
+#define MA_CASE(JJ) case JJ: multiaxpy_kernel<JJ, NORM><<<blocks, kRedThreads, 0, ctx->stream>>>(V, ld, j0, h, w, n, ctx->d_red); break;
+    switch (J) {
+        MA_CASE(1) MA_CASE(2) MA_CASE(3) MA_CASE(4) MA_CASE(5) MA_CASE(6) MA_CASE(7) MA_CASE(8)
+    }
+#undef MA_CASE
+    ctx->launches++;
+}
+
 int fedmx_multiaxpy_norm(fedmx_ctx *ctx, const double *V, int64_t ld, int nvec, const double *h_dev, double *w, int64_t n,
                          double *norm2_dev) {
-    const unsigned blocks = grid_for(n, kRedThreads);
-    multiaxpy_norm_kernel<<<blocks, kRedThreads, 0, ctx->stream>>>(V, ld, nvec, h_dev, w, n, ctx->d_red);
+    const unsigned blocks = grid_for(n, kRedThreads * 2);
+    int j0 = 0;
+    while (j0 < nvec) {
+        const int J = nvec - j0 > 8 ? 8 : nvec - j0;
+        const bool last = j0 + J >= nvec;
+        if (last) launch_multiaxpy<true>(ctx, J, blocks, V, ld, j0, h_dev, w, n);
+        else launch_multiaxpy<false>(ctx, J, blocks, V, ld, j0, h_dev, w, n);
+        j0 += J;
+    }
     finish_reduce_kernel<<<1, kRedThreads, 0, ctx->stream>>>(ctx->d_red, int(blocks), norm2_dev);
-    ctx->launches += 2;
+    ctx->launches++;
     FEDMX_CHECK_CUDA(ctx, cudaGetLastError());
     return FEDMX_OK;
 }
@@ -496,6 +566,24 @@ extern "C" int fedmx_error_norm(fedmx_ctx *ctx, const double *d_new, const doubl
     FEDMX_REQUIRE(ctx, comp >= 0 && comp < ctx->n_eq, "fedmx_error_norm: bad component");
     const unsigned blocks = grid_for(ctx->n_owned, kRedThreads);
     error_norm_kernel<<<blocks, kRedThreads, 0, ctx->stream>>>(d_new, d_old, ctx->n_owned, ctx->n_eq, comp, eps, ctx->d_red);
+    finish_reduce_kernel<<<2, kRedThreads, 0, ctx->stream>>>(ctx->d_red, int(blocks), ctx->d_hess + 2048);
+    ctx->launches += 2;
+    FEDMX_CHECK_CUDA(ctx, cudaGetLastError());
+    int rc;
+    if (ctx->n_ranks > 1 && (rc = fedmx_global_sum(ctx, ctx->d_hess + 2048, 2))) return rc;
+    FEDMX_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + 2048, ctx->d_hess + 2048, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    FEDMX_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *err = sqrt(ctx->h_pinned[2048]) / sqrt(ctx->h_pinned[2049]);
+    return FEDMX_OK;
+}
+
+extern "C" int fedmx_error_norm_strided(fedmx_ctx *ctx, const double *d_new, const double *d_old, int64_t stride, int64_t offset,
+                                        int64_t n, double eps, double *err) {
+    if (!ctx) return FEDMX_EINVAL;
+    FEDMX_REQUIRE(ctx, ctx->d_red && d_new && d_old && err && stride >= 1 && offset >= 0 && offset < stride && n >= 0,
+                  "fedmx_error_norm_strided: bad arguments");
+    const unsigned blocks = grid_for(n, kRedThreads);
+    error_norm_kernel<<<blocks, kRedThreads, 0, ctx->stream>>>(d_new, d_old, n, int(stride), int(offset), eps, ctx->d_red);
     finish_reduce_kernel<<<2, kRedThreads, 0, ctx->stream>>>(ctx->d_red, int(blocks), ctx->d_hess + 2048);
     ctx->launches += 2;
     FEDMX_CHECK_CUDA(ctx, cudaGetLastError());

@@ -74,19 +74,13 @@ int gmres_impl(fedmx_ctx *ctx, const double *d_b, double *d_x, int restart, doub
                 if ((rc = fedmx_multiaxpy_norm(ctx, V, ld, k + 1, dh, w, n, dh + 64))) return rc;
                 if (multi && (rc = fedmx_global_sum(ctx, dh + 64, 1))) return rc;
             }
-            // next basis vector: V_{k+1} = w / ||w||   (norm read on the device)
-            if (k + 1 <= restart) {
-                if ((rc = fedmx_scale_copy(ctx, w, V + int64_t(k + 1) * ld, n, 1.0, nullptr))) return rc;
-            }
             FEDMX_CHECK_CUDA(ctx, cudaMemcpyAsync(hp, dh, 65 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
             FEDMX_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
             const double hk1 = sqrt(hp[64]);
             for (int i = 0; i <= k; ++i) Hm(i, k) = hp[i];
             Hm(k + 1, k) = hk1;
-            if (hk1 > 0.0) {
-                // normalise in place (scale_copy above stored the unnormalised vector)
-                if ((rc = fedmx_scale_copy(ctx, V + int64_t(k + 1) * ld, V + int64_t(k + 1) * ld, n, 1.0 / hk1, nullptr))) return rc;
-            }
+            // next basis vector: V_{k+1} = w / ||w||  (one pass, after the norm has reached the host)
+            if (hk1 > 0.0 && (rc = fedmx_scale_copy(ctx, w, V + int64_t(k + 1) * ld, n, 1.0 / hk1, nullptr))) return rc;
             for (int i = 0; i < k; ++i) {
                 const double t = cs[i] * Hm(i, k) + sn[i] * Hm(i + 1, k);
                 Hm(i + 1, k) = -sn[i] * Hm(i, k) + cs[i] * Hm(i + 1, k);

@@ -247,6 +247,12 @@ class HotPath:
         self._ck(self.lib.fedmx_error_norm(self.h, _ptr(x_new), _ptr(x_old), comp, eps, C.byref(out)))
         return out.value
 
+    def error_norm_strided(self, a, b, stride=1, offset=0, n=None, eps=3.0e-16):
+        out = C.c_double()
+        n = self.n_owned if n is None else n
+        self._ck(self.lib.fedmx_error_norm_strided(self.h, _ptr(a), _ptr(b), stride, offset, n, eps, C.byref(out)))
+        return out.value
+
     def interp_table(self, x, kx, ky, out, divisor=1.0, x_stride=1, out_stride=1, n=None):
         n = (x.numel() // x_stride) if n is None else n
         self._ck(self.lib.fedmx_interp_table(self.h, _ptr(x), x_stride, n, _ptr(kx), _ptr(ky), kx.numel(), divisor,
@@ -287,6 +293,16 @@ class HotPath:
 
     def halo_exchange(self, vec, n_comp=None):
         self._ck(self.lib.fedmx_halo_exchange(self.h, _ptr(vec), self.n_eq if n_comp is None else n_comp))
+
+
+def pi34_step(dt, err, tol, dt_min, dt_max):
+    e = (C.c_double * 3)(*[float(v) for v in list(err)[:3]] + [1.0] * max(0, 3 - len(err)))
+    return float(_l.load().fedmx_pi34_step(dt, e, tol, dt_min, dt_max))
+
+
+def h211b_step(dt, dt_old, err, tol, dt_min, dt_max):
+    e = (C.c_double * 3)(*[float(v) for v in list(err)[:3]] + [1.0] * max(0, 3 - len(err)))
+    return float(_l.load().fedmx_h211b_step(dt, dt_old, e, tol, dt_min, dt_max))
 
 
 def pid_step(dt, err, tol, dt_min, dt_max):

@@ -50,6 +50,7 @@ SIGNATURES = {
     "fedmx_newton_solve": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_void_p,
                                      C.c_int, C.POINTER(NewtonParams), C.POINTER(NewtonResult)]),
     "fedmx_error_norm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, c_dp]),
+    "fedmx_error_norm_strided": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_double, c_dp]),
     "fedmx_pid_step": (C.c_double, [C.c_double, c_dp, C.c_double, C.c_double, C.c_double]),
     "fedmx_pi34_step": (C.c_double, [C.c_double, c_dp, C.c_double, C.c_double, C.c_double]),
     "fedmx_h211b_step": (C.c_double, [C.c_double, C.c_double, c_dp, C.c_double, C.c_double, C.c_double]),

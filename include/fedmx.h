@@ -162,6 +162,9 @@ int fedmx_newton_solve(fedmx_ctx *ctx, double *d_x, double dt, double dt_old, do
 /* err = ||a - b + eps||_2 / ||b + eps||_2 over component comp of two node-interleaved vectors
  * (fedm/functions.py:1062-1064; eps = DOLFIN_EPS added entry-wise). */
 int fedmx_error_norm(fedmx_ctx *ctx, const double *d_new, const double *d_old, int comp, double eps, double *err);
+/* Same estimator on arbitrary strided views (per-field vectors: stride 1, offset 0), n entries (owned nodes). */
+int fedmx_error_norm_strided(fedmx_ctx *ctx, const double *d_new, const double *d_old, int64_t stride, int64_t offset,
+                             int64_t n, double eps, double *err);
 /* PID / PI.3.4 / H211b controllers (fedm/functions.py:915-951); host libm, bit-exact with the reference. */
 double fedmx_pid_step(double dt, const double err[3], double tol, double dt_min, double dt_max);
 double fedmx_pi34_step(double dt, const double err[3], double tol, double dt_min, double dt_max);

@@ -1,0 +1,132 @@
+"""CPU tests of the reference-named API layer (no GPU): the reference's own unit tests for
+modify_approximation_vars (tests/unit_tests/functions/test_modify_approximation_vars.py:6-54, restated), the
+controllers, the readers on the reference's input decks, and adaptive_solver's accept/reject logic driven by a
+scripted fake solver (log format, retry factors, SystemExit)."""
+import numpy as np
+import pytest
+
+from fedm_b200 import file_io, functions as F
+
+
+def test_modify_approximation_vars_lfa_drops_first_species():
+    ns, ne, sp, m, c = F.modify_approximation_vars("LFA", 3, ["a", "b", "c"], [1.0, 2.0, 3.0], [0.0, 1.0, -1.0])
+    assert (ns, ne, sp, m, c) == (2, 3, ["b", "c"], [2.0, 3.0], [1.0, -1.0])
+
+
+def test_modify_approximation_vars_lmea_keeps_all():
+    ns, ne, sp, m, c = F.modify_approximation_vars("LMEA", 3, ["a", "b", "c"], [1.0, 2.0, 3.0], [0.0, 1.0, -1.0])
+    assert (ns, ne, sp) == (3, 4, ["a", "b", "c"]) and m == [1.0, 2.0, 3.0] and c == [0.0, 1.0, -1.0]
+
+
+def test_modify_approximation_vars_bad_name():
+    with pytest.raises(ValueError) as exc:
+        F.modify_approximation_vars("hello world", 3, ["a"], [1.0], [0.0])
+    assert "hello world" in str(exc.value)
+
+
+def test_controllers_match_python_formulas():
+    e = [2.3e-4, 1.9e-4, 2.8e-4]
+    ref = 1e-12 * ((e[1] / e[0]) ** 0.075 * (1e-3 / e[0]) ** 0.175 * (e[1] ** 2 / (e[0] * e[2])) ** 0.01)
+    assert F.adaptive_timestep(1e-12, e, 1e-3, 1e-15, 1.0) == ref
+    ref = 1e-12 * ((0.8 * 1e-3 / e[0]) ** (0.3 / 3) * (0.8 * e[1] / e[0]) ** (0.4 / 3))
+    assert F.adaptive_timestep_PI34(1e-12, e, 1e-3, 1e-15, 1.0) == ref
+    ref = 1e-12 * ((0.8 * 1e-3 / e[0]) ** (1 / 12) * (0.8 * 1e-3 / e[1]) ** (1 / 12) * (1e-12 / 2e-12) ** (-1 / 4))
+    assert F.adaptive_timestep_H211b(1e-12, 2e-12, e, 1e-3, 1e-15, 1.0) == ref
+
+
+def test_readers_on_reference_decks(golden_dir):
+    file_io.files.file_input = golden_dir / "glow_discharge_input"
+    path = file_io.files.file_input / "4_particles"
+    n, names, props, stems = file_io.read_speclist(path)
+    assert (n, names, stems) == (4, ["Ar[1p0]", "Ar[*]", "Ar[+]", "e"], ["Ar_1p0", "Ar_star", "Ar_plus", "electrons"])
+    M, Z = file_io.read_particle_properties(props, "4_particles")
+    assert Z == [0.0, 0.0, 1.0, -1.0] and M[3] == 9.10938215e-31
+    P, L, G = file_io.reaction_matrices(path, names)
+    assert P.tolist() == [[1, 0, 0, 1], [1, 0, 0, 1], [0, 1, 0, 1], [0, 1, 0, 1], [0, 2, 0, 0], [0, 1, 0, 0], [1, 0, 0, 1]]
+    assert (G - L).tolist() == [[-1, 1, 0, 0], [-1, 0, 1, 1], [1, -1, 0, 0], [0, -1, 1, 1], [1, -2, 1, 1], [0, -1, 0, 0], [0, 0, 0, 0]]
+    assert file_io.read_energy_loss(path) == [11.55, 15.76, -11.55, 4.21, -7.34, 0.0, 1.0]
+    kf = file_io.rate_coefficient_file_names(path)
+    deps = file_io.read_dependences(kf)
+    assert deps == ["Umean"] * 4 + ["const", "const", "Umean"]
+    kx, ky = file_io.read_rate_coefficients(kf, deps)
+    assert len(kx[0]) == 353 and ky[4] == 0.81e-15 and ky[5] == 1e6
+    mx, my, md = file_io.read_transport_coefficients(stems, "mobility", "4_particles")
+    assert md == [0, 0, "E/N", "Umean"] and my[0] == 0 and len(mx[2]) == 306
+    dx, dy, dd = file_io.read_transport_coefficients(stems, "Diffusion", "4_particles")
+    assert dd == ["const", "const", "ESR", "Umean"] and dy[1] == 1.738e20
+    file_io.files.file_input = golden_dir / "streamer_discharge_input"
+    sx, sy, sd = file_io.read_transport_coefficients(["ions", "e"], "mobility", "benchmark_model")
+    assert sd == ["const.", "fun:E"] and sy[1] == "2.3987*E_m**(-0.26)"
+    with pytest.raises(RuntimeError):
+        file_io.files.file_input = golden_dir / "does_not_exist"
+
+
+class _FakeVec:
+    def __init__(self, hot):
+        self.hot, self.t, self.n_comp = hot, None, 1
+
+
+class _FakeFn:
+    def __init__(self, hot):
+        self._v = _FakeVec(hot)
+        self.assigned = 0
+
+    def vector(self):
+        return self._v
+
+    def assign(self, other):
+        self.assigned += 1
+
+
+class _FakeHot:
+    n_owned = 10
+
+    def __init__(self, errors):
+        self.errors = list(errors)
+
+    def error_norm_strided(self, a, b, stride, offset, n, eps):
+        assert eps == 3.0e-16 and n == 10
+        return self.errors.pop(0)
+
+
+class _FakeSolver:
+    def __init__(self, fail_on):
+        self.calls, self.fail_on = 0, set(fail_on)
+
+    def solve(self, problem, x):
+        self.calls += 1
+        if self.calls in self.fail_on:
+            raise RuntimeError("Newton solver did not converge")
+        return 3, True
+
+
+class _Assigner:
+    def assign(self, a, b):
+        pass
+
+
+def test_adaptive_solver_accept_reject_and_log(tmp_path):
+    from fedm_b200.dolfin_shim import Expression
+    hot = _FakeHot([5e-3, 4e-4])                 # first attempt too inaccurate, third attempt accepted
+    solver = _FakeSolver(fail_on={2})            # second attempt: Newton failure
+    dt, dt_old = Expression("time_step", time_step=4e-12), Expression("time_step", time_step=1e30)
+    u_new, u_old = _FakeFn(hot), _FakeFn(hot)
+    new, old = [_FakeFn(hot), _FakeFn(hot), _FakeFn(hot)], [_FakeFn(hot), _FakeFn(hot), _FakeFn(hot)]
+    error, max_error = [0.0, 0.0], [1, 1, 1]
+    log = tmp_path / "relative error.log"
+
+    class P:
+        t = 0.0
+    t = F.adaptive_solver(solver, P(), 1e-9, dt, dt_old, u_new, u_old, new, old, _Assigner(), error, log, max_error, 1e-3, 1e-15,
+                          time_dependent_arguments=[], approximation="LFA")
+    dt1 = 4e-12 * (0.5 * 1e-3 / 5e-3)            # error >= ttol: dt *= 0.5*ttol/max_error
+    dt2 = dt1 * 0.5                              # exception: dt *= 0.5
+    assert dt.time_step == dt2 and t == 1e-9 + dt2 and solver.calls == 3 and u_new.assigned == 2
+    rows = log.read_text().splitlines(keepends=True)
+    assert rows == [f"{5e-3:<23}  {1e30:<23}  {4e-12:<23}\n", f"{4e-4:<23}  {1e30:<23}  {dt2:<23}\n"]
+    assert max_error[0] == 4e-4
+    # below dt_min the program terminates, as in the reference
+    hot2 = _FakeHot([1.0] * 50)
+    with pytest.raises(SystemExit):
+        F.adaptive_solver(_FakeSolver(()), P(), 0.0, Expression("time_step", time_step=1e-14), dt_old, u_new, u_old, new, old,
+                          _Assigner(), [0.0], log, [1, 1, 1], 1e-3, 1e-15, approximation="LMEA")
