@@ -4,10 +4,9 @@
 // 2 pi r grad(u).grad(v) (reference: fedm/functions.py:401) depends on the mesh only -- and uploaded level by
 // level; every operator (A_l, P_l, R_l) is stored in scalar SELL-32 so that all V-cycle kernels are coalesced,
 // HBM-bound streaming kernels (one thread per row).  Preconditioner application for r = (r_T, r_Phi):
-//     z   = Dinv r                       node-block Jacobi (transport part kept)
-//     rr  = r_Phi - A_{Phi,T} z_T        partial block SpMV (2 of n_eq^2 entry planes)
-//     z_Phi = Vcycle(rr)
-// i.e. a block lower-triangular (CPR-like) preconditioner.  PETSc's role here is PCApply inside KSPGMRES
+//     z     = Dinv r                     node-block Jacobi (all components; captures the node-local coupling)
+//     z_Phi = Vcycle(r_Phi)              multigrid on the elliptic component
+// i.e. a block-diagonal two-stage (CPR-like) preconditioner.  PETSc's role here is PCApply inside KSPGMRES
 // (reference call site fedm/functions.py:1047); results do not depend on the preconditioner, only iteration counts.
 #include <algorithm>
 
@@ -59,29 +58,94 @@ __global__ void dense_matvec_kernel(const double *__restrict__ M, const double *
     if (lane == 0) y[row] = acc;
 }
 
-// rr[i] = r[NEQ*i+comp] - sum_j sum_{l != comp} A[(i,j)][comp][l] z[NEQ*j+l]     (owned columns only when local_only)
+// z = Dinv r (node-block Jacobi) and, in the same pass, rhs_c[i] = r[NEQ*i + comp] (right-hand side of the AMG stage)
 template <int NEQ>
-__global__ void __launch_bounds__(128) phi_residual_kernel(SellView S, const double *__restrict__ val,
-                                                           const double *__restrict__ r, const double *__restrict__ z,
-                                                           int comp, int64_t n_local_cols, double *__restrict__ rr) {
+__global__ void __launch_bounds__(128) dinv_extract_kernel(SellView S, const double *__restrict__ dinv, const double *__restrict__ r,
+                                                           int comp, double *__restrict__ z, double *__restrict__ rhs_c) {
     constexpr int NB = NEQ * NEQ;
     const int64_t row = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (row >= S.n_rows) return;
     const int64_t s = row / FEDMX_SLICE;
     const int lane = int(row % FEDMX_SLICE);
-    if (s >= S.n_slices) return;
-    const int width = S.slice_width[s];
-    const int64_t gbase = S.slice_ptr[s];
-    double acc = 0.0;
-    for (int k = 0; k < width; ++k) {
-        const int64_t slot = gbase + int64_t(k) * FEDMX_SLICE;
-        const int32_t c = S.col[slot + lane];
-        if (c >= n_local_cols) continue;
-        const double *v = val + slot * NB + lane;
+    const double *d = dinv + s * FEDMX_SLICE * NB + lane;
+    double in[NEQ];
 #pragma unroll
-        for (int l = 0; l < NEQ; ++l)
-            if (l != comp) acc = fma(__ldcs(v + (comp * NEQ + l) * FEDMX_SLICE), __ldg(z + int64_t(NEQ) * c + l), acc);
+    for (int l = 0; l < NEQ; ++l) in[l] = r[int64_t(NEQ) * row + l];
+#pragma unroll
+    for (int i = 0; i < NEQ; ++i) {
+        double acc = 0.0;
+#pragma unroll
+        for (int l = 0; l < NEQ; ++l) acc = fma(d[(i * NEQ + l) * FEDMX_SLICE], in[l], acc);
+        z[int64_t(NEQ) * row + i] = acc;
+        if (i == comp) rhs_c[row] = in[i];
     }
-    if (row < S.n_rows) rr[row] = r[int64_t(NEQ) * row + comp] - acc;
+}
+
+// ---- fused coarse levels: one CTA walks levels [first, last] of the V-cycle with __syncthreads() between the phases
+struct CoarseLevelDev {
+    int64_t n, n_coarse;
+    double omega;
+    ScalarSell A, P, R;
+    const double *dinv;
+    double *b, *x, *x2, *r;
+};
+
+__device__ __forceinline__ double ssell_row(const ScalarSell &M, int64_t row, const double *x) {
+    const int64_t s = row / FEDMX_SLICE;
+    const int lane = int(row % FEDMX_SLICE);
+    const int width = M.slice_width[s];
+    const int64_t base = M.slice_ptr[s] + lane;
+    double t = 0.0;
+    for (int k = 0; k < width; ++k) {
+        const int64_t e = base + int64_t(k) * FEDMX_SLICE;
+        t = fma(M.val[e], x[M.col[e]], t);
+    }
+    return t;
+}
+
+__global__ void __launch_bounds__(1024) coarse_vcycle_kernel(const CoarseLevelDev *L, int nl, int nu, const double *__restrict__ cinv) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    // down: pre-smooth (zero initial guess), residual, restriction.  The current iterate always ends up in lv.x.
+    for (int l = 0; l < nl - 1; ++l) {
+        const CoarseLevelDev &lv = L[l];
+        for (int64_t i = tid; i < lv.n; i += nt) lv.x[i] = lv.omega * lv.dinv[i] * lv.b[i];
+        __syncthreads();
+        for (int sweep = 1; sweep < nu; ++sweep) {
+            for (int64_t i = tid; i < lv.n; i += nt) lv.x2[i] = lv.x[i] + lv.omega * lv.dinv[i] * (lv.b[i] - ssell_row(lv.A, i, lv.x));
+            __syncthreads();
+            for (int64_t i = tid; i < lv.n; i += nt) lv.x[i] = lv.x2[i];
+            __syncthreads();
+        }
+        for (int64_t i = tid; i < lv.n; i += nt) lv.r[i] = lv.b[i] - ssell_row(lv.A, i, lv.x);
+        __syncthreads();
+        for (int64_t i = tid; i < lv.n_coarse; i += nt) L[l + 1].b[i] = ssell_row(lv.R, i, lv.r);
+        __syncthreads();
+    }
+    {   // coarsest level: dense inverse, one warp per row
+        const CoarseLevelDev &lc = L[nl - 1];
+        const int n = int(lc.n);
+        const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+        for (int row = warp; row < n; row += nw) {
+            double acc = 0.0;
+            for (int j = lane; j < n; j += 32) acc = fma(cinv[int64_t(row) * n + j], lc.b[j], acc);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) lc.x[row] = acc;
+        }
+        __syncthreads();
+    }
+    // up: prolongation + correction, post-smooth
+    for (int l = nl - 2; l >= 0; --l) {
+        const CoarseLevelDev &lv = L[l];
+        for (int64_t i = tid; i < lv.n; i += nt) lv.x[i] += ssell_row(lv.P, i, L[l + 1].x);
+        __syncthreads();
+        for (int sweep = 0; sweep < nu; ++sweep) {
+            for (int64_t i = tid; i < lv.n; i += nt) lv.x2[i] = lv.x[i] + lv.omega * lv.dinv[i] * (lv.b[i] - ssell_row(lv.A, i, lv.x));
+            __syncthreads();
+            for (int64_t i = tid; i < lv.n; i += nt) lv.x[i] = lv.x2[i];
+            __syncthreads();
+        }
+    }
 }
 
 __global__ void comp_scatter_kernel(const double *__restrict__ e, double *__restrict__ z, int neq, int comp, int64_t n) {
@@ -133,42 +197,65 @@ void launch_ssell(fedmx_ctx *ctx, const ScalarSell &A, const double *x, const do
 
 }  // namespace
 
+// Levels with at most kFuseRows rows are walked by the single-CTA kernel (they are launch-latency bound otherwise).
+constexpr int64_t kFuseRows = 3000;   // larger levels are faster as separate launches (one CTA is latency-bound on the gathers)
+
+static int setup_coarse_fusion(fedmx_ctx *ctx) {
+    auto &L = ctx->amg_levels;
+    const int nl = int(L.size());
+    int first = nl - 1;
+    while (first > 0 && L[first - 1].n <= kFuseRows) --first;
+    if (ctx->n_ranks > 1 && first == 0) first = 1;          // the finest level of a partitioned run needs halo exchanges
+    if (first > nl - 1) first = nl - 1;
+    std::vector<CoarseLevelDev> h(nl - first);
+    for (int l = first; l < nl; ++l) {
+        CoarseLevelDev &d = h[l - first];
+        d.n = L[l].n; d.n_coarse = L[l].n_coarse; d.omega = L[l].omega;
+        d.A = L[l].A; d.P = L[l].P; d.R = L[l].R;
+        d.dinv = L[l].dinv; d.b = L[l].b; d.x = L[l].x; d.x2 = L[l].x2; d.r = L[l].r;
+    }
+    CoarseLevelDev *dev;
+    int rc = fedmx_dev_alloc(ctx, &dev, h.size());
+    if (rc) return rc;
+    FEDMX_CHECK_CUDA(ctx, cudaMemcpy(dev, h.data(), h.size() * sizeof(CoarseLevelDev), cudaMemcpyHostToDevice));
+    ctx->d_coarse_levels = dev;
+    ctx->coarse_first = first;
+    ctx->coarse_count = nl - first;
+    return FEDMX_OK;
+}
+
 // One V-cycle with zero initial guess: x_0 = Vcycle(b_0); b_0 = levels[0].b, result in levels[0].x
 int fedmx_amg_vcycle(fedmx_ctx *ctx) {
     auto &L = ctx->amg_levels;
     const int nl = int(L.size());
     FEDMX_REQUIRE(ctx, nl > 0 && ctx->amg_coarse_inv, "AMG hierarchy not set");
     const int nu = ctx->amg_nu;
-    for (int l = 0; l < nl - 1; ++l) {
+    int rc;
+    if (ctx->coarse_first < 0 && (rc = setup_coarse_fusion(ctx))) return rc;
+    const int cf = ctx->coarse_first;
+    for (int l = 0; l < cf; ++l) {
         AmgLevel &lv = L[l];
         const unsigned vb = unsigned((lv.n + 255) / 256);
         first_sweep_kernel<<<vb, 256, 0, ctx->stream>>>(lv.b, lv.dinv, lv.omega, lv.x, lv.n);
         ctx->launches++;
         for (int sweep = 1; sweep < nu; ++sweep) {
-            int rc;
             if (l == 0 && ctx->n_ranks > 1 && (rc = fedmx_halo_exchange_internal(ctx, lv.x, 1))) return rc;
             launch_ssell<MODE_JACOBI>(ctx, lv.A, lv.x, lv.b, lv.dinv, lv.omega, lv.x2);
             std::swap(lv.x, lv.x2);
         }
         const bool dist = (l == 0 && ctx->n_ranks > 1);
-        int rc;
         if (dist && (rc = fedmx_halo_exchange_internal(ctx, lv.x, 1))) return rc;      // ghosts of x for A x
         launch_ssell<MODE_RESID>(ctx, lv.A, lv.x, lv.b, nullptr, 0.0, lv.r);
         launch_ssell<MODE_MULT>(ctx, lv.R, lv.r, nullptr, nullptr, 0.0, L[l + 1].b);
         // distributed fine level: R holds only this rank's fine columns; the coarse right-hand side is the sum over ranks
         if (dist && (rc = fedmx_global_sum(ctx, L[l + 1].b, int(L[l + 1].n)))) return rc;
     }
-    {
-        AmgLevel &lc = L[nl - 1];
-        const int n = int(lc.n);
-        dense_matvec_kernel<<<(n * 32 + 127) / 128, 128, 0, ctx->stream>>>(ctx->amg_coarse_inv, lc.b, lc.x, n);
-        ctx->launches++;
-    }
-    for (int l = nl - 2; l >= 0; --l) {
+    coarse_vcycle_kernel<<<1, 1024, 0, ctx->stream>>>((const CoarseLevelDev *)ctx->d_coarse_levels, ctx->coarse_count, nu, ctx->amg_coarse_inv);
+    ctx->launches++;
+    for (int l = cf - 1; l >= 0; --l) {
         AmgLevel &lv = L[l];
         launch_ssell<MODE_ADD>(ctx, lv.P, L[l + 1].x, nullptr, nullptr, 0.0, lv.x);
         for (int sweep = 0; sweep < nu; ++sweep) {
-            int rc;
             if (l == 0 && ctx->n_ranks > 1 && (rc = fedmx_halo_exchange_internal(ctx, lv.x, 1))) return rc;
             launch_ssell<MODE_JACOBI>(ctx, lv.A, lv.x, lv.b, lv.dinv, lv.omega, lv.x2);
             std::swap(lv.x, lv.x2);
@@ -189,16 +276,16 @@ int fedmx_precond_apply(fedmx_ctx *ctx, const double *d_r, double *d_z) {
     const int comp = ctx->amg_comp;
     const int64_t n = ctx->n_owned;
     const int threads = 128;
-    const unsigned blocks = unsigned((ctx->sell.n_slices * FEDMX_SLICE + threads - 1) / threads);
+    // block-diagonal two-stage preconditioner: z = Dinv r on every node block, then the potential component is replaced
+    // by the multigrid solve of its own residual.  (The block-triangular variants with an extra A_{Phi,T} pass give the
+    // same Krylov counts on this problem -- the node-local coupling is already inside Dinv -- and cost a partial SpMV.)
     if (ctx->n_eq == 1) {
         FEDMX_CHECK_CUDA(ctx, cudaMemcpyAsync(l0.b, d_r, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     } else {
-        if ((rc = fedmx_apply_dinv(ctx, d_r, d_z))) return rc;
-        if (ctx->n_ranks > 1 && (rc = fedmx_halo_exchange_internal(ctx, d_z, ctx->n_eq))) return rc;
-        const int64_t ncols = ctx->n_vertices;
+        const unsigned nb = unsigned((n + threads - 1) / threads);
         switch (ctx->n_eq) {
-            case 3: phi_residual_kernel<3><<<blocks, threads, 0, ctx->stream>>>(ctx->sell, ctx->d_val, d_r, d_z, comp, ncols, l0.b); break;
-            case 5: phi_residual_kernel<5><<<blocks, threads, 0, ctx->stream>>>(ctx->sell, ctx->d_val, d_r, d_z, comp, ncols, l0.b); break;
+            case 3: dinv_extract_kernel<3><<<nb, threads, 0, ctx->stream>>>(ctx->sell, ctx->d_dinv, d_r, comp, d_z, l0.b); break;
+            case 5: dinv_extract_kernel<5><<<nb, threads, 0, ctx->stream>>>(ctx->sell, ctx->d_dinv, d_r, comp, d_z, l0.b); break;
             default: ctx->err = "two-stage preconditioner: unsupported n_eq"; return FEDMX_EUNSUPPORTED;
         }
         ctx->launches++;
@@ -215,6 +302,8 @@ extern "C" int fedmx_amg_reset(fedmx_ctx *ctx) {
     ctx->amg_levels.clear();      // device memory stays owned by the context until destroy
     ctx->amg_coarse_inv = nullptr;
     ctx->precond_kind = 0;
+    ctx->coarse_first = -1;
+    ctx->coarse_count = 0;
     return FEDMX_OK;
 }
 
@@ -272,6 +361,7 @@ extern "C" int fedmx_precond_set(fedmx_ctx *ctx, int kind, int comp, int nu) {
     ctx->precond_kind = kind;
     ctx->amg_comp = comp;
     ctx->amg_nu = nu;
+    ctx->coarse_first = -1;
     return FEDMX_OK;
 }
 

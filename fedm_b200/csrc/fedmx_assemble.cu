@@ -384,16 +384,20 @@ struct ProjectionModel {
 // =====================================================================================================
 // Generic row kernel
 // =====================================================================================================
-template <int NB>
-__device__ __forceinline__ void store_block(double *val, int64_t group_base, int slot, int lane, const double *blk) {
-    double *dst = val + (group_base + int64_t(slot) * FEDMX_SLICE) * NB + lane;
+template <int NEQ>
+__device__ __forceinline__ void store_block(const AsmArgs &A, int64_t group_base, int slot, int lane, const double *blk) {
+    constexpr int NB = NEQ * NEQ;
+    const int64_t g = group_base + int64_t(slot) * FEDMX_SLICE;
+    double *dst = A.val + g * NB + lane;
 #pragma unroll
     for (int e = 0; e < NB; ++e) dst[e * FEDMX_SLICE] = blk[e];
 }
 
-template <int NB>
-__device__ __forceinline__ void add_block(double *val, int64_t group_base, int slot, int lane, const double *blk) {
-    double *dst = val + (group_base + int64_t(slot) * FEDMX_SLICE) * NB + lane;
+template <int NEQ>
+__device__ __forceinline__ void add_block(const AsmArgs &A, int64_t group_base, int slot, int lane, const double *blk) {
+    constexpr int NB = NEQ * NEQ;
+    const int64_t g = group_base + int64_t(slot) * FEDMX_SLICE;
+    double *dst = A.val + g * NB + lane;
 #pragma unroll
     for (int e = 0; e < NB; ++e) dst[e * FEDMX_SLICE] += blk[e];
 }
@@ -458,13 +462,13 @@ __global__ void __launch_bounds__(128, MINB) assemble_rows_kernel(AsmArgs A) {
             for (int q = 0; q < NB; ++q) carry[q] += o.J[1][q];
             if (bc) zero_row<NEQ>(carry, bc_comp);
             // block (i, vp) is complete (or the partial first block of a closed fan): write it
-            store_block<NB>(A.val, gbase, PACK_SLOT_P(pack), lane, carry);
+            store_block<NEQ>(A, gbase, PACK_SLOT_P(pack), lane, carry);
 #pragma unroll
             for (int q = 0; q < NB; ++q) carry[q] = o.J[2][q];
             if (PACK_LAST(pack)) {
                 if (bc) zero_row<NEQ>(carry, bc_comp);
-                if (PACK_CLOSED(pack)) add_block<NB>(A.val, gbase, PACK_SLOT_N(pack), lane, carry);
-                else store_block<NB>(A.val, gbase, PACK_SLOT_N(pack), lane, carry);
+                if (PACK_CLOSED(pack)) add_block<NEQ>(A, gbase, PACK_SLOT_N(pack), lane, carry);
+                else store_block<NEQ>(A, gbase, PACK_SLOT_N(pack), lane, carry);
             }
         }
     }
@@ -481,7 +485,7 @@ __global__ void __launch_bounds__(128, MINB) assemble_rows_kernel(AsmArgs A) {
                 if (k == bc_comp) diag[k * NEQ + k] = 1.0;
         }
     }
-    if (JAC) store_block<NB>(A.val, gbase, diag_slot, lane, diag);
+    if (JAC) store_block<NEQ>(A, gbase, diag_slot, lane, diag);
     if (A.res) {
 #pragma unroll
         for (int k = 0; k < NEQ; ++k) A.res[int64_t(NEQ) * row + k] = R[k];

@@ -114,6 +114,8 @@ struct fedmx_ctx {
     std::vector<AmgLevel> amg_levels;
     double *amg_coarse_inv = nullptr;
     double *d_tmp = nullptr;
+    void *d_coarse_levels = nullptr;   // device array of fused coarse-level descriptors
+    int coarse_first = -1, coarse_count = 0;
     // profiling (CUDA events around kernel classes)
     bool prof_on = false;
     std::vector<cudaEvent_t> prof_ev[5];     // start/stop pairs per kind
