@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(128) ssell_kernel(ScalarSell A, const double *
     double t = 0.0;
     for (int k = 0; k < width; ++k) {
         const int64_t e = base + int64_t(k) * FEDMX_SLICE;
-        t = fma(A.val[e], __ldg(x + A.col[e]), t);
+        t = fma(double(A.val[e]), __ldg(x + A.col[e]), t);
     }
     if (row >= A.n_rows) return;
     if (MODE == MODE_MULT) y[row] = t;
@@ -98,7 +98,7 @@ __device__ __forceinline__ double ssell_row(const ScalarSell &M, int64_t row, co
     double t = 0.0;
     for (int k = 0; k < width; ++k) {
         const int64_t e = base + int64_t(k) * FEDMX_SLICE;
-        t = fma(M.val[e], x[M.col[e]], t);
+        t = fma(double(M.val[e]), x[M.col[e]], t);
     }
     return t;
 }
@@ -168,17 +168,17 @@ int upload_ssell(fedmx_ctx *ctx, ScalarSell &M, int64_t n_rows, int64_t n_cols, 
         sp[s + 1] = sp[s] + int64_t(w) * FEDMX_SLICE;
     }
     std::vector<int32_t> c(sp[M.n_slices], 0);
-    std::vector<double> v(sp[M.n_slices], 0.0);
+    std::vector<float> v(sp[M.n_slices], 0.0f);
     for (int64_t r = 0; r < n_rows; ++r) {
         const int64_t s = r / FEDMX_SLICE, l = r % FEDMX_SLICE;
         for (int32_t q = rowptr[r]; q < rowptr[r + 1]; ++q) {
             const int64_t e = sp[s] + int64_t(q - rowptr[r]) * FEDMX_SLICE + l;
             c[e] = col[q];
-            v[e] = val[q];
+            v[e] = float(val[q]);
         }
     }
     int rc;
-    int64_t *dsp; int32_t *dsw, *dc; double *dv;
+    int64_t *dsp; int32_t *dsw, *dc; float *dv;
     if ((rc = fedmx_upload(ctx, &dsp, sp))) return rc;
     if ((rc = fedmx_upload(ctx, &dsw, sw))) return rc;
     if ((rc = fedmx_upload(ctx, &dc, c))) return rc;

@@ -58,7 +58,9 @@ struct ScalarSell {
     const int64_t *slice_ptr = nullptr;
     const int32_t *slice_width = nullptr;
     const int32_t *col = nullptr;
-    const double *val = nullptr;
+    const float *val = nullptr;     // multigrid operators are stored in FP32 (vectors and arithmetic stay FP64): the
+                                    // preconditioner is still one fixed linear operator, so GMRES is unaffected, and
+                                    // the V-cycle moves 8 instead of 12 bytes per nonzero
 };
 
 struct AmgLevel {
