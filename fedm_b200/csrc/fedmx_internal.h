@@ -112,6 +112,7 @@ struct fedmx_ctx {
     double *h_pinned = nullptr;  // pinned host scratch
     int64_t red_blocks = 0;
     // preconditioner: 0 = node-block Jacobi, 1 = two-stage (AMG on component amg_comp + block Jacobi)
+    int newton_expected_its = 0;   // Newton iterations of the previous converged solve (predictor for speculative J assembly)
     int precond_kind = 0, amg_comp = 0, amg_nu = 1;
     std::vector<AmgLevel> amg_levels;
     double *amg_coarse_inv = nullptr;

@@ -147,16 +147,26 @@ extern "C" int fedmx_newton_solve(fedmx_ctx *ctx, double *d_x, double dt, double
     const int64_t n = int64_t(ctx->n_eq) * ctx->n_owned;
     const bool multi = ctx->n_ranks > 1;
     *res = fedmx_newton_result{};
+    // SNES evaluates F(x_k) for the convergence test and then J(x_k).  The row kernel produces both in one pass, so the
+    // Jacobian is assembled speculatively together with the residual while further iterations are expected (the
+    // iteration count of the previous solve is the predictor); otherwise the cheaper residual-only kernel runs first.
+    const int expected = ctx->newton_expected_its > 0 ? ctx->newton_expected_its : 1 << 30;
+    auto evaluate = [&](int k, bool *have_jac) -> int {
+        const bool fused = k < expected && k < prm->max_it;
+        *have_jac = fused;
+        return fedmx_assemble_internal(ctx, d_x, dt, dt_old, t, h_bc_values, n_bc_values, ctx->d_res, fused);
+    };
+    bool have_jac = false;
     if (multi && (rc = fedmx_halo_exchange_internal(ctx, d_x, ctx->n_eq))) return rc;
-    if ((rc = fedmx_assemble_internal(ctx, d_x, dt, dt_old, t, h_bc_values, n_bc_values, ctx->d_res, false))) return rc;
+    if ((rc = evaluate(0, &have_jac))) return rc;
     double fnorm;
     if ((rc = fedmx_norm2_local(ctx, ctx->d_res, n, &fnorm, true))) return rc;
     res->fnorm0 = res->fnorm = fnorm;
     res->fnorm_history[0] = fnorm;
     if (!(fnorm == fnorm) || isinf(fnorm)) { res->reason = FEDMX_SNES_DIVERGED_FNORM_NAN; return FEDMX_OK; }
-    if (fnorm < prm->atol) { res->reason = FEDMX_SNES_CONVERGED_FNORM_ABS; return FEDMX_OK; }
+    if (fnorm < prm->atol) { res->reason = FEDMX_SNES_CONVERGED_FNORM_ABS; ctx->newton_expected_its = 0; return FEDMX_OK; }
     for (int it = 1; it <= prm->max_it; ++it) {
-        if ((rc = fedmx_assemble_internal(ctx, d_x, dt, dt_old, t, h_bc_values, n_bc_values, nullptr, true))) return rc;
+        if (!have_jac && (rc = fedmx_assemble_internal(ctx, d_x, dt, dt_old, t, h_bc_values, n_bc_values, nullptr, true))) return rc;
         if ((rc = fedmx_update_block_jacobi(ctx))) return rc;
         int kits = 0, kconv = 0;
         double krn = 0.0;
@@ -167,17 +177,21 @@ extern "C" int fedmx_newton_solve(fedmx_ctx *ctx, double *d_x, double dt, double
         if (!kconv) { res->reason = FEDMX_SNES_DIVERGED_LINEAR_SOLVE; return FEDMX_OK; }
         if ((rc = fedmx_axpy(ctx, -1.0, ctx->d_dx, d_x, n))) return rc;      // x <- x - delta (full step)
         if (multi && (rc = fedmx_halo_exchange_internal(ctx, d_x, ctx->n_eq))) return rc;
-        if ((rc = fedmx_assemble_internal(ctx, d_x, dt, dt_old, t, h_bc_values, n_bc_values, ctx->d_res, false))) return rc;
+        if ((rc = evaluate(it, &have_jac))) return rc;
         if ((rc = fedmx_norm2_local(ctx, ctx->d_res, n, &fnorm, true))) return rc;
         res->fnorm = fnorm;
         if (it < 64) res->fnorm_history[it] = fnorm;
         if (!(fnorm == fnorm) || isinf(fnorm)) { res->reason = FEDMX_SNES_DIVERGED_FNORM_NAN; return FEDMX_OK; }
-        if (fnorm < prm->atol) { res->reason = FEDMX_SNES_CONVERGED_FNORM_ABS; return FEDMX_OK; }
-        if (fnorm <= prm->rtol * res->fnorm0) { res->reason = FEDMX_SNES_CONVERGED_FNORM_RELATIVE; return FEDMX_OK; }
-        double dxn, xn;
-        if ((rc = fedmx_norm2_local(ctx, ctx->d_dx, n, &dxn, true))) return rc;
-        if ((rc = fedmx_norm2_local(ctx, d_x, n, &xn, true))) return rc;
-        if (dxn < prm->stol * xn) { res->reason = FEDMX_SNES_CONVERGED_SNORM_RELATIVE; return FEDMX_OK; }
+        bool done = false;
+        if (fnorm < prm->atol) { res->reason = FEDMX_SNES_CONVERGED_FNORM_ABS; done = true; }
+        else if (fnorm <= prm->rtol * res->fnorm0) { res->reason = FEDMX_SNES_CONVERGED_FNORM_RELATIVE; done = true; }
+        else {
+            double dxn, xn;
+            if ((rc = fedmx_norm2_local(ctx, ctx->d_dx, n, &dxn, true))) return rc;
+            if ((rc = fedmx_norm2_local(ctx, d_x, n, &xn, true))) return rc;
+            if (dxn < prm->stol * xn) { res->reason = FEDMX_SNES_CONVERGED_SNORM_RELATIVE; done = true; }
+        }
+        if (done) { ctx->newton_expected_its = it; return FEDMX_OK; }
     }
     res->reason = FEDMX_SNES_DIVERGED_MAX_IT;
     return FEDMX_OK;
