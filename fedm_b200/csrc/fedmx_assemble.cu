@@ -33,22 +33,24 @@ struct AsmArgs {
     const double *coords;   // [n_vertices][2]
     const double *x;        // [n_vertices][n_eq]
     const double *fields;   // [n_vertices][n_fields]
+    const double *nodal;    // [n_vertices][NC] library-owned per-node precomputations of the model (may be null)
     double *val;            // matrix values (may be null for residual-only)
     double *res;            // residual (may be null)
     ModelParams mp;
 };
 
 // One vertex as seen by a model: coordinates, unknowns, coefficient fields.
-template <int NEQ, int NF>
+template <int NEQ, int NF, int NC = 0>
 struct Vtx {
     int32_t id;             // local vertex index (FFC orients non-symmetric quadrature rules by ascending index)
     double r, z;
     double u[NEQ];
     double f[NF > 0 ? NF : 1];
+    double c[NC > 0 ? NC : 1];
 };
 
-template <int NEQ, int NF>
-__device__ __forceinline__ void load_vertex(const AsmArgs &A, int32_t v, Vtx<NEQ, NF> &o) {
+template <int NEQ, int NF, int NC>
+__device__ __forceinline__ void load_vertex(const AsmArgs &A, int32_t v, Vtx<NEQ, NF, NC> &o) {
     const double2 c = *reinterpret_cast<const double2 *>(A.coords + 2 * int64_t(v));
     o.id = v;
     o.r = c.x;
@@ -57,6 +59,8 @@ __device__ __forceinline__ void load_vertex(const AsmArgs &A, int32_t v, Vtx<NEQ
     for (int k = 0; k < NEQ; ++k) o.u[k] = __ldg(A.x + int64_t(NEQ) * v + k);
 #pragma unroll
     for (int k = 0; k < NF; ++k) o.f[k] = __ldg(A.fields + int64_t(NF) * v + k);
+#pragma unroll
+    for (int k = 0; k < NC; ++k) o.c[k] = __ldg(A.nodal + int64_t(NC) * v + k);
 }
 
 // Row `a` of one element tensor, local vertex order (a, p, n) = (0, 1, 2).
@@ -77,13 +81,15 @@ struct RowOut {
 // fields: [0]=hist_i [1]=hist_e  (BDF2 history, fedmx_bdf2_history)
 // =====================================================================================================
 struct StreamerModel {
-    static constexpr int MINB = 3, MINB_RES = 4;
+    static constexpr int MINB = 2, MINB_RES = 4;
     static constexpr int NEQ = 3;
     static constexpr int NF = 2;
+    static constexpr int NC = 2;      // nodal c_s = exp(u_s/6): e^{u(q)} at the 3-point rule is a product of them
+    typedef Vtx<3, 2, 2> V;
 
     // facet (a,b): b is local vertex LB (1 = p, 2 = n), c the opposite vertex
     template <bool JAC, int LB>
-    static __device__ __forceinline__ void facet(const Vtx<3, 2> &a, const Vtx<3, 2> &b, const Vtx<3, 2> &c, const double *gr,
+    static __device__ __forceinline__ void facet(const V &a, const V &b, const V &c, const double *gr,
                                                  const double *gz, double Gr, double Gz, double iEm, double mu, double dmu,
                                                  RowOut<3> &o) {
         const double tr_ = b.r - a.r, tz_ = b.z - a.z;
@@ -112,8 +118,8 @@ struct StreamerModel {
     }
 
     template <bool JAC>
-    static __device__ __forceinline__ void row(const ModelParams &mp, const Vtx<3, 2> &a, const Vtx<3, 2> &p,
-                                               const Vtx<3, 2> &n, uint32_t mk_ap, uint32_t mk_an,
+    static __device__ __forceinline__ void row(const ModelParams &mp, const V &a, const V &p,
+                                               const V &n, uint32_t mk_ap, uint32_t mk_an,
                                                RowOut<3> &o) {
         // --- geometry (fedm uses x[0] = r, x[1] = z)
         const double e1r = p.r - a.r, e1z = p.z - a.z, e2r = n.r - a.r, e2z = n.z - a.z;
@@ -156,6 +162,11 @@ struct StreamerModel {
         double Ri = 0, Re = 0, Rphi_s = 0, Wsum = 0, Mne0 = 0, Mne = 0;
         double Mii[3] = {0, 0, 0}, Mne2[3] = {0, 0, 0}, Mee[3] = {0, 0, 0}, Mni2[3] = {0, 0, 0}, Nb[3] = {0, 0, 0};
         const double w0 = adet * (1.0 / 6.0) * kTwoPi;
+        // e^{u(q)} with u(q) = (u_a+u_p+u_n)/6 + u_q/2  ==  (c_a c_p c_n) c_q^3,  c_v = exp(u_v/6) precomputed per node:
+        // 6 exp() per cell visit become a handful of multiplications
+        const double Ti = a.c[0] * p.c[0] * n.c[0], Te = a.c[1] * p.c[1] * n.c[1];
+        const double ci3[3] = {a.c[0] * a.c[0] * a.c[0], p.c[0] * p.c[0] * p.c[0], n.c[0] * n.c[0] * n.c[0]};
+        const double ce3[3] = {a.c[1] * a.c[1] * a.c[1], p.c[1] * p.c[1] * p.c[1], n.c[1] * n.c[1] * n.c[1]};
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
             const double l0 = (q == 0) ? (2.0 / 3.0) : (1.0 / 6.0);
@@ -167,7 +178,7 @@ struct StreamerModel {
             const double ue = l0 * a.u[1] + l1 * p.u[1] + l2 * n.u[1];
             const double hi = l0 * a.f[0] + l1 * p.f[0] + l2 * n.f[0];
             const double he = l0 * a.f[1] + l1 * p.f[1] + l2 * n.f[1];
-            const double ni = exp(ui), ne = exp(ue);
+            const double ni = Ti * ci3[q], ne = Te * ce3[q];
             const double bi = ct * ui + hi, be = ct * ue + he;
             const double Wni = W * ni, Wne = W * ne;
             Ri += (Wni * bi - S * Wne) * l0;
@@ -230,6 +241,7 @@ struct StreamerModel {
 // =====================================================================================================
 struct PoissonModel {
     static constexpr int MINB = 2, MINB_RES = 2;
+    static constexpr int NC = 0;
     static constexpr int NEQ = 1;
     static constexpr int NF = 2;
 
@@ -276,6 +288,7 @@ struct PoissonModel {
 // =====================================================================================================
 struct TofModel {
     static constexpr int MINB = 2, MINB_RES = 2;
+    static constexpr int NC = 0;
     static constexpr int NEQ = 1;
     static constexpr int NF = 1;
 
@@ -345,6 +358,7 @@ struct TofModel {
 // =====================================================================================================
 struct ProjectionModel {
     static constexpr int MINB = 2, MINB_RES = 2;
+    static constexpr int NC = 0;
     static constexpr int NEQ = 1;
     static constexpr int NF = 1;
 
@@ -415,7 +429,7 @@ __device__ __forceinline__ void zero_row(double *blk, int comp) {
 
 template <class Model, bool JAC, int MINB>
 __global__ void __launch_bounds__(128, MINB) assemble_rows_kernel(AsmArgs A) {
-    constexpr int NEQ = Model::NEQ, NF = Model::NF, NB = NEQ * NEQ;
+    constexpr int NEQ = Model::NEQ, NF = Model::NF, NC = Model::NC, NB = NEQ * NEQ;
     const int64_t row = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     const int64_t s = row / FEDMX_SLICE;
     const int lane = int(row % FEDMX_SLICE);
@@ -430,8 +444,8 @@ __global__ void __launch_bounds__(128, MINB) assemble_rows_kernel(AsmArgs A) {
     const int64_t ibase = A.S.inc_ptr[s];
     const int width = A.S.inc_width[s];
 
-    Vtx<NEQ, NF> va;
-    if (active) load_vertex<NEQ, NF>(A, int32_t(row), va);
+    Vtx<NEQ, NF, NC> va;
+    if (active) load_vertex<NEQ, NF, NC>(A, int32_t(row), va);
 
     double diag[NB], carry[NB], R[NEQ];
 #pragma unroll
@@ -439,14 +453,26 @@ __global__ void __launch_bounds__(128, MINB) assemble_rows_kernel(AsmArgs A) {
 #pragma unroll
     for (int k = 0; k < NEQ; ++k) R[k] = 0.0;
 
+    // Walk the fan.  Consecutive cells of a fan share an edge, so the "previous" vertex of cell m+1 is the "next" vertex
+    // of cell m: only ONE new vertex is gathered per cell (its indices are fetched one cell ahead).
+    Vtx<NEQ, NF, NC> p, n;
+    int32_t vp1 = 0, vn1 = 0;
+    uint32_t pack0 = 0, pack1 = 0;
+    if (n_inc > 0) {
+        const int64_t e = ibase + lane;
+        const int32_t vp0 = A.S.inc_vp[e], vn0 = A.S.inc_vn[e];
+        pack0 = A.S.inc_pack[e];
+        load_vertex<NEQ, NF, NC>(A, vp0, p);
+        load_vertex<NEQ, NF, NC>(A, vn0, n);
+    }
     for (int m = 0; m < width; ++m) {
         if (m >= n_inc) continue;
-        const int64_t e = ibase + int64_t(m) * FEDMX_SLICE + lane;
-        const int32_t vp = A.S.inc_vp[e], vn = A.S.inc_vn[e];
-        const uint32_t pack = A.S.inc_pack[e];
-        Vtx<NEQ, NF> p, n;
-        load_vertex<NEQ, NF>(A, vp, p);
-        load_vertex<NEQ, NF>(A, vn, n);
+        const uint32_t pack = pack0;
+        const bool has1 = m + 1 < n_inc;
+        if (has1) {                                                      // indices of cell m+1
+            const int64_t e = ibase + int64_t(m + 1) * FEDMX_SLICE + lane;
+            vp1 = A.S.inc_vp[e]; vn1 = A.S.inc_vn[e]; pack1 = A.S.inc_pack[e];
+        }
         RowOut<NEQ> o;
         Model::template row<JAC>(A.mp, va, p, n, PACK_MK_N(pack), PACK_MK_P(pack), o);
 #pragma unroll
@@ -471,6 +497,12 @@ __global__ void __launch_bounds__(128, MINB) assemble_rows_kernel(AsmArgs A) {
                 else store_block<NEQ>(A, gbase, PACK_SLOT_N(pack), lane, carry);
             }
         }
+        if (has1) {
+            if (PACK_FIRST(pack1)) load_vertex<NEQ, NF, NC>(A, vp1, p);  // a new fan starts (non-manifold vertex): rare
+            else p = n;
+            load_vertex<NEQ, NF, NC>(A, vn1, n);
+        }
+        pack0 = pack1;
     }
     if (!active) return;
     if (bc) {
@@ -502,9 +534,28 @@ __global__ void bdf2_history_kernel(int64_t n_nodes, int n_eq, int n_hist, const
     fields[v * n_fields + field_offset + k] = c_old * x_old[v * n_eq + k] + c_old1 * x_old1[v * n_eq + k];
 }
 
+// c_s = exp(u_s / 6) for the first NC components of every local vertex (StreamerModel)
+__global__ void nodal_exp6_kernel(const double *__restrict__ x, int n_eq, int nc, int64_t n_nodes, double *__restrict__ out) {
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n_nodes * nc) return;
+    const int64_t v = i / nc;
+    const int k = int(i % nc);
+    out[i] = exp(x[v * n_eq + k] * (1.0 / 6.0));
+}
+
 template <class Model>
 int launch_assembly(fedmx_ctx *ctx, const double *d_x, double *d_b, bool jac) {
     AsmArgs A;
+    if (Model::NC > 0) {
+        if (!ctx->d_nodal) {
+            int rc = fedmx_dev_alloc(ctx, &ctx->d_nodal, size_t(ctx->n_vertices) * Model::NC);
+            if (rc) return rc;
+        }
+        const int64_t cnt = ctx->n_vertices * Model::NC;
+        nodal_exp6_kernel<<<unsigned((cnt + 255) / 256), 256, 0, ctx->stream>>>(d_x, Model::NEQ, Model::NC, ctx->n_vertices, ctx->d_nodal);
+        ctx->launches++;
+    }
+    A.nodal = ctx->d_nodal;
     A.S = ctx->sell;
     A.coords = ctx->d_coords;
     A.x = d_x;
@@ -518,7 +569,7 @@ int launch_assembly(fedmx_ctx *ctx, const double *d_x, double *d_b, bool jac) {
     ProfScope prof(ctx, jac ? FEDMX_PROF_ASM_JAC : FEDMX_PROF_ASM_RES);
     // resident CTAs per SM the kernel is compiled for (register cap 65536/(128*MINB)); FEDMX_ASM_MINB overrides for tuning
     static const int env_minb = getenv("FEDMX_ASM_MINB") ? atoi(getenv("FEDMX_ASM_MINB")) : 0;
-    // measured on B200 at 10 M DOF (tools/bench_assembly.py): Jacobian 1.48/1.22/1.49 ms and residual 1.02/0.86/0.77 ms
+    // measured on B200 at 10 M DOF (tools/bench_assembly.py): Jacobian 1.07/1.13/1.51 ms and residual 0.76/0.57/0.56 ms
     // for 2/3/4 resident CTAs per SM
     const int minb = env_minb ? env_minb : (jac ? Model::MINB : Model::MINB_RES);
     if (jac) {

@@ -101,6 +101,7 @@ struct fedmx_ctx {
     // model
     ModelParams mp{};
     const double *d_fields = nullptr;
+    double *d_nodal = nullptr;   // library-owned per-node precomputations of the model (e.g. exp(u/6))
     // Dirichlet
     std::vector<int32_t> bc_nodes, bc_value_index;
     int bc_comp = -1;

@@ -79,6 +79,7 @@ template <int N> __device__ __forceinline__ Dual<N> dabs(const Dual<N> &a) {
 
 struct GlowModel {
     static constexpr int MINB = 2, MINB_RES = 2;
+    static constexpr int NC = 0;
     static constexpr int NEQ = 5;
     static constexpr int NF = 28;
     static constexpr int ND = 15;
