@@ -13,62 +13,11 @@
 // Storage is SELL-32 with entry-major groups (fedmx_internal.h): the 32 lanes of a warp own 32 consecutive
 // rows, so every store instruction writes 256 contiguous bytes.
 // Dirichlet rows are fused into the epilogue: b_i = x_i - g, Jacobian row = unit row (pattern kept).
-#include <math.h>
-#include <stdlib.h>
-
-#include "fedmx_internal.h"
 #include "quadrature_tables.h"
 
+#include "row_kernel.cuh"
+
 namespace {
-
-constexpr double kTwoPi = 6.283185307179586476925286766559;
-
-// Gauss-Legendre nodes on [0,1]
-__device__ __constant__ double kGL2_t[2] = {0.21132486540518711775, 0.78867513459481288225};
-__device__ __constant__ double kGL3_t[3] = {0.11270166537925831148, 0.5, 0.88729833462074168852};
-__device__ __constant__ double kGL3_w[3] = {0.27777777777777777778, 0.44444444444444444444, 0.27777777777777777778};
-
-struct AsmArgs {
-    SellView S;
-    const double *coords;   // [n_vertices][2]
-    const double *x;        // [n_vertices][n_eq]
-    const double *fields;   // [n_vertices][n_fields]
-    const double *nodal;    // [n_vertices][NC] library-owned per-node precomputations of the model (may be null)
-    double *val;            // matrix values (may be null for residual-only)
-    double *res;            // residual (may be null)
-    ModelParams mp;
-};
-
-// One vertex as seen by a model: coordinates, unknowns, coefficient fields.
-template <int NEQ, int NF, int NC = 0>
-struct Vtx {
-    int32_t id;             // local vertex index (FFC orients non-symmetric quadrature rules by ascending index)
-    double r, z;
-    double u[NEQ];
-    double f[NF > 0 ? NF : 1];
-    double c[NC > 0 ? NC : 1];
-};
-
-template <int NEQ, int NF, int NC>
-__device__ __forceinline__ void load_vertex(const AsmArgs &A, int32_t v, Vtx<NEQ, NF, NC> &o) {
-    const double2 c = *reinterpret_cast<const double2 *>(A.coords + 2 * int64_t(v));
-    o.id = v;
-    o.r = c.x;
-    o.z = c.y;
-#pragma unroll
-    for (int k = 0; k < NEQ; ++k) o.u[k] = __ldg(A.x + int64_t(NEQ) * v + k);
-#pragma unroll
-    for (int k = 0; k < NF; ++k) o.f[k] = __ldg(A.fields + int64_t(NF) * v + k);
-#pragma unroll
-    for (int k = 0; k < NC; ++k) o.c[k] = __ldg(A.nodal + int64_t(NC) * v + k);
-}
-
-// Row `a` of one element tensor, local vertex order (a, p, n) = (0, 1, 2).
-template <int NEQ>
-struct RowOut {
-    double R[NEQ];
-    double J[3][NEQ * NEQ];   // J[b][k*NEQ + l] = d R_a[k] / d U_b[l]
-};
 
 // =====================================================================================================
 // Streamer model (LFA, N_eq = 3: ln n_i, ln n_e, Phi).
@@ -395,135 +344,6 @@ struct ProjectionModel {
 
 #include "glow_model.cuh"
 
-// =====================================================================================================
-// Generic row kernel
-// =====================================================================================================
-template <int NEQ>
-__device__ __forceinline__ void store_block(const AsmArgs &A, int64_t group_base, int slot, int lane, const double *blk) {
-    constexpr int NB = NEQ * NEQ;
-    const int64_t g = group_base + int64_t(slot) * FEDMX_SLICE;
-    double *dst = A.val + g * NB + lane;
-#pragma unroll
-    for (int e = 0; e < NB; ++e) dst[e * FEDMX_SLICE] = blk[e];
-}
-
-template <int NEQ>
-__device__ __forceinline__ void add_block(const AsmArgs &A, int64_t group_base, int slot, int lane, const double *blk) {
-    constexpr int NB = NEQ * NEQ;
-    const int64_t g = group_base + int64_t(slot) * FEDMX_SLICE;
-    double *dst = A.val + g * NB + lane;
-#pragma unroll
-    for (int e = 0; e < NB; ++e) dst[e * FEDMX_SLICE] += blk[e];
-}
-
-// Zero block row `comp` with static register indices (comp is a run-time value: a dynamic index would push the
-// accumulators into local memory).
-template <int NEQ>
-__device__ __forceinline__ void zero_row(double *blk, int comp) {
-#pragma unroll
-    for (int k = 0; k < NEQ; ++k)
-#pragma unroll
-        for (int l = 0; l < NEQ; ++l)
-            if (k == comp) blk[k * NEQ + l] = 0.0;
-}
-
-template <class Model, bool JAC, int MINB>
-__global__ void __launch_bounds__(128, MINB) assemble_rows_kernel(AsmArgs A) {
-    constexpr int NEQ = Model::NEQ, NF = Model::NF, NC = Model::NC, NB = NEQ * NEQ;
-    const int64_t row = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    const int64_t s = row / FEDMX_SLICE;
-    const int lane = int(row % FEDMX_SLICE);
-    if (s >= A.S.n_slices) return;
-    const bool active = row < A.S.n_rows;
-    const uint32_t rp = A.S.row_pack[row];
-    const int n_inc = active ? int(rp & 0xffu) : 0;
-    const int diag_slot = int((rp >> 8) & 0xffu);
-    const int bc = int(rp >> 16);                   // value index + 1, 0 = unconstrained
-    const int bc_comp = A.mp.bc_comp;
-    const int64_t gbase = A.S.slice_ptr[s];
-    const int64_t ibase = A.S.inc_ptr[s];
-    const int width = A.S.inc_width[s];
-
-    Vtx<NEQ, NF, NC> va;
-    if (active) load_vertex<NEQ, NF, NC>(A, int32_t(row), va);
-
-    double diag[NB], carry[NB], R[NEQ];
-#pragma unroll
-    for (int e = 0; e < NB; ++e) { diag[e] = 0.0; carry[e] = 0.0; }
-#pragma unroll
-    for (int k = 0; k < NEQ; ++k) R[k] = 0.0;
-
-    // Walk the fan.  Consecutive cells of a fan share an edge, so the "previous" vertex of cell m+1 is the "next" vertex
-    // of cell m: only ONE new vertex is gathered per cell (its indices are fetched one cell ahead).
-    Vtx<NEQ, NF, NC> p, n;
-    int32_t vp1 = 0, vn1 = 0;
-    uint32_t pack0 = 0, pack1 = 0;
-    if (n_inc > 0) {
-        const int64_t e = ibase + lane;
-        const int32_t vp0 = A.S.inc_vp[e], vn0 = A.S.inc_vn[e];
-        pack0 = A.S.inc_pack[e];
-        load_vertex<NEQ, NF, NC>(A, vp0, p);
-        load_vertex<NEQ, NF, NC>(A, vn0, n);
-    }
-    for (int m = 0; m < width; ++m) {
-        if (m >= n_inc) continue;
-        const uint32_t pack = pack0;
-        const bool has1 = m + 1 < n_inc;
-        if (has1) {                                                      // indices of cell m+1
-            const int64_t e = ibase + int64_t(m + 1) * FEDMX_SLICE + lane;
-            vp1 = A.S.inc_vp[e]; vn1 = A.S.inc_vn[e]; pack1 = A.S.inc_pack[e];
-        }
-        RowOut<NEQ> o;
-        Model::template row<JAC>(A.mp, va, p, n, PACK_MK_N(pack), PACK_MK_P(pack), o);
-#pragma unroll
-        for (int k = 0; k < NEQ; ++k) R[k] += o.R[k];
-        if (JAC) {
-#pragma unroll
-            for (int q = 0; q < NB; ++q) diag[q] += o.J[0][q];
-            if (PACK_FIRST(pack)) {
-#pragma unroll
-                for (int q = 0; q < NB; ++q) carry[q] = 0.0;
-            }
-#pragma unroll
-            for (int q = 0; q < NB; ++q) carry[q] += o.J[1][q];
-            if (bc) zero_row<NEQ>(carry, bc_comp);
-            // block (i, vp) is complete (or the partial first block of a closed fan): write it
-            store_block<NEQ>(A, gbase, PACK_SLOT_P(pack), lane, carry);
-#pragma unroll
-            for (int q = 0; q < NB; ++q) carry[q] = o.J[2][q];
-            if (PACK_LAST(pack)) {
-                if (bc) zero_row<NEQ>(carry, bc_comp);
-                if (PACK_CLOSED(pack)) add_block<NEQ>(A, gbase, PACK_SLOT_N(pack), lane, carry);
-                else store_block<NEQ>(A, gbase, PACK_SLOT_N(pack), lane, carry);
-            }
-        }
-        if (has1) {
-            if (PACK_FIRST(pack1)) load_vertex<NEQ, NF, NC>(A, vp1, p);  // a new fan starts (non-manifold vertex): rare
-            else p = n;
-            load_vertex<NEQ, NF, NC>(A, vn1, n);
-        }
-        pack0 = pack1;
-    }
-    if (!active) return;
-    if (bc) {
-        const double g = A.mp.bc_values[bc - 1];
-#pragma unroll
-        for (int k = 0; k < NEQ; ++k)
-            if (k == bc_comp) R[k] = va.u[k] - g;
-        if (JAC) {
-            zero_row<NEQ>(diag, bc_comp);
-#pragma unroll
-            for (int k = 0; k < NEQ; ++k)
-                if (k == bc_comp) diag[k * NEQ + k] = 1.0;
-        }
-    }
-    if (JAC) store_block<NEQ>(A, gbase, diag_slot, lane, diag);
-    if (A.res) {
-#pragma unroll
-        for (int k = 0; k < NEQ; ++k) A.res[int64_t(NEQ) * row + k] = R[k];
-    }
-}
-
 __global__ void bdf2_history_kernel(int64_t n_nodes, int n_eq, int n_hist, const double *__restrict__ x_old,
                                     const double *__restrict__ x_old1, double c_old, double c_old1,
                                     double *__restrict__ fields, int n_fields, int field_offset) {
@@ -556,6 +376,7 @@ int launch_assembly(fedmx_ctx *ctx, const double *d_x, double *d_b, bool jac) {
         ctx->launches++;
     }
     A.nodal = ctx->d_nodal;
+    for (int k = 0; k < FEDMX_MAX_REFS; ++k) A.refs[k] = ctx->plugin_refs[k];
     A.S = ctx->sell;
     A.coords = ctx->d_coords;
     A.x = d_x;
@@ -563,24 +384,13 @@ int launch_assembly(fedmx_ctx *ctx, const double *d_x, double *d_b, bool jac) {
     A.val = jac ? ctx->d_val : nullptr;
     A.res = d_b;
     A.mp = ctx->mp;
-    const int threads = 128;
-    const int64_t rows = ctx->sell.n_slices * FEDMX_SLICE;
-    const unsigned blocks = unsigned((rows + threads - 1) / threads);
     ProfScope prof(ctx, jac ? FEDMX_PROF_ASM_JAC : FEDMX_PROF_ASM_RES);
-    // resident CTAs per SM the kernel is compiled for (register cap 65536/(128*MINB)); FEDMX_ASM_MINB overrides for tuning
-    static const int env_minb = getenv("FEDMX_ASM_MINB") ? atoi(getenv("FEDMX_ASM_MINB")) : 0;
+    // resident CTAs per SM the kernel is compiled for (register cap 65536/(128*MINB)); FEDMX_ASM_MINB overrides for tuning.
     // measured on B200 at 10 M DOF (tools/bench_assembly.py): Jacobian 1.07/1.13/1.51 ms and residual 0.76/0.57/0.56 ms
     // for 2/3/4 resident CTAs per SM
+    static const int env_minb = getenv("FEDMX_ASM_MINB") ? atoi(getenv("FEDMX_ASM_MINB")) : 0;
     const int minb = env_minb ? env_minb : (jac ? Model::MINB : Model::MINB_RES);
-    if (jac) {
-        if (minb >= 4) assemble_rows_kernel<Model, true, 4><<<blocks, threads, 0, ctx->stream>>>(A);
-        else if (minb == 3) assemble_rows_kernel<Model, true, 3><<<blocks, threads, 0, ctx->stream>>>(A);
-        else assemble_rows_kernel<Model, true, 2><<<blocks, threads, 0, ctx->stream>>>(A);
-    } else {
-        if (minb >= 4) assemble_rows_kernel<Model, false, 4><<<blocks, threads, 0, ctx->stream>>>(A);
-        else if (minb == 3) assemble_rows_kernel<Model, false, 3><<<blocks, threads, 0, ctx->stream>>>(A);
-        else assemble_rows_kernel<Model, false, 2><<<blocks, threads, 0, ctx->stream>>>(A);
-    }
+    launch_rows<Model>(A, jac, minb, ctx->stream);
     ctx->launches++;
     FEDMX_CHECK_CUDA(ctx, cudaGetLastError());
     return FEDMX_OK;
@@ -592,7 +402,7 @@ int assemble_dispatch(fedmx_ctx *ctx, const double *d_x, double dt, double dt_ol
     FEDMX_REQUIRE(ctx, ctx->mp.model_id != 0, "assemble: no model");
     FEDMX_REQUIRE(ctx, d_x != nullptr, "assemble: null state");
     FEDMX_REQUIRE(ctx, n_bc_values >= 0 && n_bc_values < FEDMX_MAX_BC, "assemble: too many Dirichlet values");
-    FEDMX_REQUIRE(ctx, ctx->mp.n_fields == 0 || ctx->d_fields, "assemble: coefficient fields not bound");
+    FEDMX_REQUIRE(ctx, ctx->mp.n_fields == 0 || ctx->d_fields || ctx->mp.model_id == FEDMX_MODEL_PLUGIN, "assemble: coefficient fields not bound");
     ctx->mp.dt = dt;
     ctx->mp.dt_old = dt_old;
     ctx->mp.t = t;
@@ -609,6 +419,25 @@ int assemble_dispatch(fedmx_ctx *ctx, const double *d_x, double dt, double dt_ol
             return launch_assembly<GlowModel>(ctx, d_x, d_b, jac);
         case FEDMX_MODEL_PROJECTION:
             return launch_assembly<ProjectionModel>(ctx, d_x, d_b, jac);
+        case FEDMX_MODEL_PLUGIN: {
+            FEDMX_REQUIRE(ctx, ctx->plugin_launch, "assemble: no plug-in loaded");
+            AsmArgs A;
+            A.S = ctx->sell;
+            A.coords = ctx->d_coords;
+            A.x = d_x;
+            A.fields = nullptr;
+            A.nodal = nullptr;
+            for (int k = 0; k < FEDMX_MAX_REFS; ++k) A.refs[k] = ctx->plugin_refs[k];
+            A.val = jac ? ctx->d_val : nullptr;
+            A.res = d_b;
+            A.mp = ctx->mp;
+            ProfScope prof(ctx, jac ? FEDMX_PROF_ASM_JAC : FEDMX_PROF_ASM_RES);
+            int rc = ctx->plugin_launch(&A, jac ? 1 : 0, 2, (void *)ctx->stream);
+            ctx->launches++;
+            if (rc) { ctx->err = "assemble: plug-in launch failed"; return FEDMX_ECUDA; }
+            FEDMX_CHECK_CUDA(ctx, cudaGetLastError());
+            return FEDMX_OK;
+        }
         default:
             ctx->err = "assemble: model not implemented";
             return FEDMX_EUNSUPPORTED;
@@ -626,6 +455,11 @@ extern "C" int fedmx_model_set(fedmx_ctx *ctx, int model_id, int n_params, const
     if (!ctx) return FEDMX_EINVAL;
     FEDMX_REQUIRE(ctx, n_params >= 0 && n_params <= FEDMX_MAX_PARAMS, "fedmx_model_set: too many parameters");
     int neq = 0, nf = 0;
+    if (model_id == FEDMX_MODEL_PLUGIN) {
+        FEDMX_REQUIRE(ctx, ctx->plugin_launch, "fedmx_model_set: load the plug-in first (fedmx_plugin_load)");
+        for (int i = 0; i < FEDMX_MAX_PARAMS; ++i) ctx->mp.p[i] = i < n_params ? h_params[i] : 0.0;
+        return FEDMX_OK;
+    }
     switch (model_id) {
         case FEDMX_MODEL_STREAMER: neq = StreamerModel::NEQ; nf = StreamerModel::NF; break;
         case FEDMX_MODEL_POISSON: neq = PoissonModel::NEQ; nf = PoissonModel::NF; break;
@@ -683,5 +517,36 @@ extern "C" int fedmx_bdf2_history(fedmx_ctx *ctx, int n_hist, const double *d_x_
         ctx->n_vertices, ctx->n_eq, n_hist, d_x_old, d_x_old1, c_old, c_old1, d_fields, n_fields, field_offset);
     ctx->launches++;
     FEDMX_CHECK_CUDA(ctx, cudaGetLastError());
+    return FEDMX_OK;
+}
+
+#include <dlfcn.h>
+
+// Load a row kernel generated by the form compiler (fedm_b200/formcompiler.py).  The .so exports
+//   int fedmx_plugin_launch(const void *asm_args, int jac, int minb, void *stream);  int fedmx_plugin_neq(); int fedmx_plugin_nf();
+extern "C" int fedmx_plugin_load(fedmx_ctx *ctx, const char *path) {
+    if (!ctx || !path) return FEDMX_EINVAL;
+    void *h = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+    if (!h) { ctx->err = std::string("fedmx_plugin_load: ") + dlerror(); return FEDMX_EINVAL; }
+    auto launch = (int (*)(const void *, int, int, void *))dlsym(h, "fedmx_plugin_launch");
+    auto neq = (int (*)())dlsym(h, "fedmx_plugin_neq");
+    auto nf = (int (*)())dlsym(h, "fedmx_plugin_nf");
+    auto sz = (int (*)())dlsym(h, "fedmx_plugin_args_size");
+    FEDMX_REQUIRE(ctx, launch && neq && nf && sz, "fedmx_plugin_load: the library does not export the plug-in entry points");
+    FEDMX_REQUIRE(ctx, sz() == int(sizeof(AsmArgs)), "fedmx_plugin_load: plug-in was built against a different libfedmx (AsmArgs size)");
+    FEDMX_REQUIRE(ctx, ctx->n_eq == 0 || ctx->n_eq == neq(), "fedmx_plugin_load: n_eq of mesh and plug-in differ");
+    FEDMX_REQUIRE(ctx, nf() <= FEDMX_MAX_REFS, "fedmx_plugin_load: too many coefficient fields");
+    ctx->plugin_handle = h;
+    ctx->plugin_launch = launch;
+    ctx->mp.model_id = FEDMX_MODEL_PLUGIN;
+    ctx->mp.n_eq = neq();
+    ctx->mp.n_fields = nf();
+    return FEDMX_OK;
+}
+
+extern "C" int fedmx_plugin_set_field(fedmx_ctx *ctx, int k, const double *d_ptr, int stride, int offset) {
+    if (!ctx) return FEDMX_EINVAL;
+    FEDMX_REQUIRE(ctx, k >= 0 && k < FEDMX_MAX_REFS && d_ptr && stride >= 1 && offset >= 0 && offset < stride, "fedmx_plugin_set_field: bad arguments");
+    ctx->plugin_refs[k] = FieldRef{d_ptr, stride, offset};
     return FEDMX_OK;
 }

@@ -11,6 +11,13 @@
 #define FEDMX_MAX_PARAMS 128
 #define FEDMX_MAX_BC 16
 #define FEDMX_SLICE 32
+#define FEDMX_MAX_REFS 48
+
+// Indirect coefficient reference of a plug-in model: component `offset` of a node-interleaved vector with `stride` comps
+struct FieldRef {
+    const double *ptr;
+    int stride, offset;
+};
 
 // Device-side view of the mesh topology in SELL-32 (sliced ELLPACK, 32 rows per slice) form.
 // Matrix block (row r = 32*s + l, k-th stored column) lives at block slot  slice_ptr[s] + 32*k + l ;
@@ -101,6 +108,10 @@ struct fedmx_ctx {
     // model
     ModelParams mp{};
     const double *d_fields = nullptr;
+    // run-time compiled model (form compiler plug-in)
+    void *plugin_handle = nullptr;
+    int (*plugin_launch)(const void *args, int jac, int minb, void *stream) = nullptr;
+    FieldRef plugin_refs[FEDMX_MAX_REFS] = {};
     double *d_nodal = nullptr;   // library-owned per-node precomputations of the model (e.g. exp(u/6))
     // Dirichlet
     std::vector<int32_t> bc_nodes, bc_value_index;

@@ -1,0 +1,213 @@
+// Generic row-assembly kernel of libfedmx, shared by the built-in models (fedmx_assemble.cu) and by the row kernels the
+// form compiler generates at run time (fedm_b200/formcompiler.py -> plug-in .so).  See fedmx_assemble.cu for the design.
+#pragma once
+#include <math.h>
+#include <stdlib.h>
+
+#include "fedmx_internal.h"
+
+namespace {
+
+constexpr double kTwoPi = 6.283185307179586476925286766559;
+
+// Gauss-Legendre nodes on [0,1]
+__device__ __constant__ double kGL2_t[2] = {0.21132486540518711775, 0.78867513459481288225};
+__device__ __constant__ double kGL3_t[3] = {0.11270166537925831148, 0.5, 0.88729833462074168852};
+__device__ __constant__ double kGL3_w[3] = {0.27777777777777777778, 0.44444444444444444444, 0.27777777777777777778};
+
+struct AsmArgs {
+    SellView S;
+    const double *coords;   // [n_vertices][2]
+    const double *x;        // [n_vertices][n_eq]
+    const double *fields;   // [n_vertices][n_fields]
+    const double *nodal;    // [n_vertices][NC] library-owned per-node precomputations of the model (may be null)
+    FieldRef refs[FEDMX_MAX_REFS];   // plug-in models: coefficient k of vertex v is refs[k].ptr[v*stride + offset]
+    double *val;            // matrix values (may be null for residual-only)
+    double *res;            // residual (may be null)
+    ModelParams mp;
+};
+
+// One vertex as seen by a model: coordinates, unknowns, coefficient fields.
+template <int NEQ, int NF, int NC = 0>
+struct Vtx {
+    int32_t id;             // local vertex index (FFC orients non-symmetric quadrature rules by ascending index)
+    double r, z;
+    double u[NEQ];
+    double f[NF > 0 ? NF : 1];
+    double c[NC > 0 ? NC : 1];
+};
+
+template <int NEQ, int NF, int NC>
+__device__ __forceinline__ void load_vertex(const AsmArgs &A, int32_t v, Vtx<NEQ, NF, NC> &o) {
+    const double2 c = *reinterpret_cast<const double2 *>(A.coords + 2 * int64_t(v));
+    o.id = v;
+    o.r = c.x;
+    o.z = c.y;
+#pragma unroll
+    for (int k = 0; k < NEQ; ++k) o.u[k] = __ldg(A.x + int64_t(NEQ) * v + k);
+    if (A.fields) {
+#pragma unroll
+        for (int k = 0; k < NF; ++k) o.f[k] = __ldg(A.fields + int64_t(NF) * v + k);
+    } else {
+#pragma unroll
+        for (int k = 0; k < NF; ++k) o.f[k] = __ldg(A.refs[k].ptr + int64_t(A.refs[k].stride) * v + A.refs[k].offset);
+    }
+#pragma unroll
+    for (int k = 0; k < NC; ++k) o.c[k] = __ldg(A.nodal + int64_t(NC) * v + k);
+}
+
+// Row `a` of one element tensor, local vertex order (a, p, n) = (0, 1, 2).
+template <int NEQ>
+struct RowOut {
+    double R[NEQ];
+    double J[3][NEQ * NEQ];   // J[b][k*NEQ + l] = d R_a[k] / d U_b[l]
+};
+
+// =====================================================================================================
+// Generic row kernel
+// =====================================================================================================
+template <int NEQ>
+__device__ __forceinline__ void store_block(const AsmArgs &A, int64_t group_base, int slot, int lane, const double *blk) {
+    constexpr int NB = NEQ * NEQ;
+    const int64_t g = group_base + int64_t(slot) * FEDMX_SLICE;
+    double *dst = A.val + g * NB + lane;
+#pragma unroll
+    for (int e = 0; e < NB; ++e) dst[e * FEDMX_SLICE] = blk[e];
+}
+
+template <int NEQ>
+__device__ __forceinline__ void add_block(const AsmArgs &A, int64_t group_base, int slot, int lane, const double *blk) {
+    constexpr int NB = NEQ * NEQ;
+    const int64_t g = group_base + int64_t(slot) * FEDMX_SLICE;
+    double *dst = A.val + g * NB + lane;
+#pragma unroll
+    for (int e = 0; e < NB; ++e) dst[e * FEDMX_SLICE] += blk[e];
+}
+
+// Zero block row `comp` with static register indices (comp is a run-time value: a dynamic index would push the
+// accumulators into local memory).
+template <int NEQ>
+__device__ __forceinline__ void zero_row(double *blk, int comp) {
+#pragma unroll
+    for (int k = 0; k < NEQ; ++k)
+#pragma unroll
+        for (int l = 0; l < NEQ; ++l)
+            if (k == comp) blk[k * NEQ + l] = 0.0;
+}
+
+template <class Model, bool JAC, int MINB>
+__global__ void __launch_bounds__(128, MINB) assemble_rows_kernel(AsmArgs A) {
+    constexpr int NEQ = Model::NEQ, NF = Model::NF, NC = Model::NC, NB = NEQ * NEQ;
+    const int64_t row = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t s = row / FEDMX_SLICE;
+    const int lane = int(row % FEDMX_SLICE);
+    if (s >= A.S.n_slices) return;
+    const bool active = row < A.S.n_rows;
+    const uint32_t rp = A.S.row_pack[row];
+    const int n_inc = active ? int(rp & 0xffu) : 0;
+    const int diag_slot = int((rp >> 8) & 0xffu);
+    const int bc = int(rp >> 16);                   // value index + 1, 0 = unconstrained
+    const int bc_comp = A.mp.bc_comp;
+    const int64_t gbase = A.S.slice_ptr[s];
+    const int64_t ibase = A.S.inc_ptr[s];
+    const int width = A.S.inc_width[s];
+
+    Vtx<NEQ, NF, NC> va;
+    if (active) load_vertex<NEQ, NF, NC>(A, int32_t(row), va);
+
+    double diag[NB], carry[NB], R[NEQ];
+#pragma unroll
+    for (int e = 0; e < NB; ++e) { diag[e] = 0.0; carry[e] = 0.0; }
+#pragma unroll
+    for (int k = 0; k < NEQ; ++k) R[k] = 0.0;
+
+    // Walk the fan.  Consecutive cells of a fan share an edge, so the "previous" vertex of cell m+1 is the "next" vertex
+    // of cell m: only ONE new vertex is gathered per cell (its indices are fetched one cell ahead).
+    Vtx<NEQ, NF, NC> p, n;
+    int32_t vp1 = 0, vn1 = 0;
+    uint32_t pack0 = 0, pack1 = 0;
+    if (n_inc > 0) {
+        const int64_t e = ibase + lane;
+        const int32_t vp0 = A.S.inc_vp[e], vn0 = A.S.inc_vn[e];
+        pack0 = A.S.inc_pack[e];
+        load_vertex<NEQ, NF, NC>(A, vp0, p);
+        load_vertex<NEQ, NF, NC>(A, vn0, n);
+    }
+    for (int m = 0; m < width; ++m) {
+        if (m >= n_inc) continue;
+        const uint32_t pack = pack0;
+        const bool has1 = m + 1 < n_inc;
+        if (has1) {                                                      // indices of cell m+1
+            const int64_t e = ibase + int64_t(m + 1) * FEDMX_SLICE + lane;
+            vp1 = A.S.inc_vp[e]; vn1 = A.S.inc_vn[e]; pack1 = A.S.inc_pack[e];
+        }
+        RowOut<NEQ> o;
+        Model::template row<JAC>(A.mp, va, p, n, PACK_MK_N(pack), PACK_MK_P(pack), o);
+#pragma unroll
+        for (int k = 0; k < NEQ; ++k) R[k] += o.R[k];
+        if (JAC) {
+#pragma unroll
+            for (int q = 0; q < NB; ++q) diag[q] += o.J[0][q];
+            if (PACK_FIRST(pack)) {
+#pragma unroll
+                for (int q = 0; q < NB; ++q) carry[q] = 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < NB; ++q) carry[q] += o.J[1][q];
+            if (bc) zero_row<NEQ>(carry, bc_comp);
+            // block (i, vp) is complete (or the partial first block of a closed fan): write it
+            store_block<NEQ>(A, gbase, PACK_SLOT_P(pack), lane, carry);
+#pragma unroll
+            for (int q = 0; q < NB; ++q) carry[q] = o.J[2][q];
+            if (PACK_LAST(pack)) {
+                if (bc) zero_row<NEQ>(carry, bc_comp);
+                if (PACK_CLOSED(pack)) add_block<NEQ>(A, gbase, PACK_SLOT_N(pack), lane, carry);
+                else store_block<NEQ>(A, gbase, PACK_SLOT_N(pack), lane, carry);
+            }
+        }
+        if (has1) {
+            if (PACK_FIRST(pack1)) load_vertex<NEQ, NF, NC>(A, vp1, p);  // a new fan starts (non-manifold vertex): rare
+            else p = n;
+            load_vertex<NEQ, NF, NC>(A, vn1, n);
+        }
+        pack0 = pack1;
+    }
+    if (!active) return;
+    if (bc) {
+        const double g = A.mp.bc_values[bc - 1];
+#pragma unroll
+        for (int k = 0; k < NEQ; ++k)
+            if (k == bc_comp) R[k] = va.u[k] - g;
+        if (JAC) {
+            zero_row<NEQ>(diag, bc_comp);
+#pragma unroll
+            for (int k = 0; k < NEQ; ++k)
+                if (k == bc_comp) diag[k * NEQ + k] = 1.0;
+        }
+    }
+    if (JAC) store_block<NEQ>(A, gbase, diag_slot, lane, diag);
+    if (A.res) {
+#pragma unroll
+        for (int k = 0; k < NEQ; ++k) A.res[int64_t(NEQ) * row + k] = R[k];
+    }
+}
+
+
+// Launch helper shared by the built-in dispatch and by plug-ins.
+template <class Model>
+inline void launch_rows(const AsmArgs &A, bool jac, int minb, cudaStream_t stream) {
+    const int threads = 128;
+    const int64_t rows = A.S.n_slices * FEDMX_SLICE;
+    const unsigned blocks = unsigned((rows + threads - 1) / threads);
+    if (jac) {
+        if (minb >= 4) assemble_rows_kernel<Model, true, 4><<<blocks, threads, 0, stream>>>(A);
+        else if (minb == 3) assemble_rows_kernel<Model, true, 3><<<blocks, threads, 0, stream>>>(A);
+        else assemble_rows_kernel<Model, true, 2><<<blocks, threads, 0, stream>>>(A);
+    } else {
+        if (minb >= 4) assemble_rows_kernel<Model, false, 4><<<blocks, threads, 0, stream>>>(A);
+        else if (minb == 3) assemble_rows_kernel<Model, false, 3><<<blocks, threads, 0, stream>>>(A);
+        else assemble_rows_kernel<Model, false, 2><<<blocks, threads, 0, stream>>>(A);
+    }
+}
+
+}  // namespace

@@ -1,0 +1,853 @@
+"""``dolfin``-named shim: the part of the dolfin 2019.1.0 Python API that FEDM's library code and example scripts touch
+(SURVEY.md Appendix E), re-implemented on top of UFL-lite (``fedm_b200.ufl``) and a compute backend.
+
+``import dolfin`` resolves here when ``compat/`` is on ``sys.path`` (see ``compat/dolfin/__init__.py``); FEDM's
+problem-definition modules (the reference's own ``fedm`` package, or this repo's mirror ``fedm_b200.functions`` /
+``fedm_b200.file_io``) then run unchanged.  All numerical work -- form compilation, assembly, Newton-Krylov -- is
+delegated to the backend: the CUDA backend (``fedm_b200.dolfin.cuda_backend``, libfedmx + JIT-compiled row kernels) is the
+product path and the default; tests may install the oracle's numpy backend to validate the shim on CPU.
+Degrees of freedom are numbered by mesh vertex (dof = n_comp*vertex + comp), not by dolfin's SCOTCH reordering.
+"""
+import math
+import os
+import re
+from pathlib import Path
+
+import numpy as np
+
+from .. import cexpr
+from .. import ufl as _ufl
+from ..mesh import TriMesh, rectangle
+from ..ufl import (Form, Measure, action, derivative, dot, exp, grad, inner, lhs, ln, rhs, sqrt)  # noqa: F401
+
+pi = math.pi
+DOLFIN_EPS = 3.0e-16
+DOLFIN_PI = math.pi
+
+_backend = None
+
+
+def set_backend(backend):
+    """Install the compute backend (tests use the oracle's numpy backend; the default is CUDA)."""
+    global _backend
+    _backend = backend
+
+
+def get_backend():
+    global _backend
+    if _backend is None:
+        from .cuda_backend import CudaBackend
+        _backend = CudaBackend()
+    return _backend
+
+
+# ---- parameters / logging / MPI ---------------------------------------------------------------------------------------
+class _Params(dict):
+    def __missing__(self, key):
+        self[key] = _Params()
+        return self[key]
+
+
+parameters = _Params()
+parameters["form_compiler"]["quadrature_degree"] = None
+
+
+def set_log_level(level):
+    pass
+
+
+class _MPI:
+    comm_world = "world"
+
+    @staticmethod
+    def rank(comm=None):
+        return int(os.environ.get("RANK", "0"))
+
+    @staticmethod
+    def size(comm=None):
+        return int(os.environ.get("WORLD_SIZE", "1"))
+
+    @staticmethod
+    def sum(comm, v):
+        return v
+
+    @staticmethod
+    def max(comm, v):
+        return v
+
+    @staticmethod
+    def min(comm, v):
+        return v
+
+
+MPI = _MPI()
+
+
+def near(a, b, eps=DOLFIN_EPS):
+    return abs(a - b) < eps
+
+
+def between(x, interval):
+    return interval[0] <= x <= interval[1]
+
+
+class Point:
+    def __init__(self, *xs):
+        self.x = tuple(float(v) for v in xs)
+
+    def __getitem__(self, i):
+        return self.x[i]
+
+
+# ---- mesh -------------------------------------------------------------------------------------------------------------
+class _Cell:
+    def __init__(self, name):
+        self.name = name
+
+
+class _Topology:
+    def __init__(self, dim):
+        self._dim = dim
+
+    def dim(self):
+        return self._dim
+
+
+class Mesh:
+    """Triangle mesh; ``Mesh('file.xml')`` reads dolfin's XML format."""
+
+    def __init__(self, source=None):
+        if isinstance(source, TriMesh):
+            self.tri = source
+        elif isinstance(source, (str, Path)):
+            self.tri = _read_dolfin_xml(source)
+        else:
+            raise TypeError("Mesh(): expected an XML file name")
+
+    def ufl_cell(self):
+        return _Cell("triangle")
+
+    def topology(self):
+        return _Topology(2)
+
+    def num_cells(self):
+        return self.tri.num_cells
+
+    def num_vertices(self):
+        return self.tri.num_vertices
+
+    def coordinates(self):
+        return self.tri.coords
+
+    def cells(self):
+        return self.tri.cells
+
+    def hmax(self):
+        return self.tri.hmax()
+
+    def hmin(self):
+        return self.tri.hmin()
+
+    def mpi_comm(self):
+        return MPI.comm_world
+
+
+def _read_dolfin_xml(path):
+    text = Path(path).read_text()
+    vs = re.findall(r'<vertex\s+index="(\d+)"\s+x="([^"]+)"\s+y="([^"]+)"', text)
+    cs = re.findall(r'<triangle\s+index="(\d+)"\s+v0="(\d+)"\s+v1="(\d+)"\s+v2="(\d+)"', text)
+    if not vs or not cs:
+        raise RuntimeError(f"Mesh: '{path}' is not a 2-D dolfin XML triangle mesh")
+    coords = np.zeros((len(vs), 2))
+    for i, x, y in vs:
+        coords[int(i)] = (float(x), float(y))
+    cells = np.zeros((len(cs), 3), dtype=np.int32)
+    for i, a, b, c in cs:
+        cells[int(i)] = sorted((int(a), int(b), int(c)))
+    return TriMesh(coords, cells)
+
+
+def RectangleMesh(p0, p1, nx, ny, diagonal="right"):
+    return Mesh(rectangle((p0[0], p0[1]), (p1[0], p1[1]), nx, ny, diagonal))
+
+
+class MeshFunction:
+    """Only the case FEDM uses: a size_t function over facets (dim-1) holding the markers of the exterior facets."""
+
+    def __init__(self, value_type, mesh, dim, value=0):
+        self.mesh, self.dim = mesh, dim
+        self.facets = mesh.tri.exterior_facets()
+        self.values = np.full(self.facets.shape[0], int(value), dtype=np.int32)
+
+    def set_all(self, value):
+        self.values[:] = int(value)
+
+    def array(self):
+        return self.values
+
+
+class SubDomain:
+    def __init__(self, *args, **kwargs):
+        pass
+
+    def inside(self, x, on_boundary):
+        return False
+
+    def mark(self, mesh_function, value):
+        """A facet is marked when all its vertices and its midpoint are inside (dolfin's check_midpoint=True)."""
+        xy = mesh_function.mesh.tri.coords
+        for f, (a, b) in enumerate(mesh_function.facets):
+            pa, pb = xy[a], xy[b]
+            if self.inside(pa, True) and self.inside(pb, True) and self.inside(0.5 * (pa + pb), True):
+                mesh_function.values[f] = int(value)
+
+
+def FacetNormal(mesh):
+    return _ufl.Vec(_ufl.Normal(0), _ufl.Normal(1))
+
+
+def _measure(kind, domain=None, subdomain_data=None, **kw):
+    return Measure(kind, domain=domain, subdomain_data=subdomain_data)
+
+
+dx = Measure("dx")
+ds = Measure("ds")
+_UflMeasure = Measure
+
+
+def Measure(kind, domain=None, subdomain_data=None, **kw):        # noqa: F811  (dolfin's constructor signature)
+    return _UflMeasure(kind, domain=domain, subdomain_data=subdomain_data)
+
+
+# ---- elements and spaces ----------------------------------------------------------------------------------------------
+class FiniteElement:
+    def __init__(self, family, cell=None, degree=1):
+        if degree != 1 or family not in ("Lagrange", "P", "CG"):
+            raise NotImplementedError("the device path implements P1 Lagrange elements on triangles")
+        self.family, self.degree, self.n = family, degree, 1
+
+
+class MixedElement:
+    def __init__(self, elements):
+        self.elements = list(elements)
+        self.n = len(self.elements)
+
+
+class FunctionSpace:
+    def __init__(self, mesh, element, degree=None, n_comp=None, vector=False):
+        if isinstance(element, str):
+            element = FiniteElement(element, None, degree)
+        self._mesh, self.element = mesh, element
+        self.n_comp = n_comp if n_comp is not None else element.n
+        self.vector = vector
+
+    def mesh(self):
+        return self._mesh
+
+    def dim(self):
+        return self.n_comp * self._mesh.num_vertices()
+
+    def sub(self, i):
+        return _SubSpace(self, i)
+
+    def num_sub_spaces(self):
+        return self.n_comp if self.n_comp > 1 else 0
+
+    def ufl_element(self):
+        return self.element
+
+
+class _SubSpace:
+    def __init__(self, parent, comp):
+        self.parent, self.comp = parent, comp
+
+
+def VectorFunctionSpace(mesh, family, degree, dim=2):
+    return FunctionSpace(mesh, FiniteElement(family, None, degree), n_comp=dim, vector=True)
+
+
+class _Indexable:
+    """Trial/test functions of a mixed space: ``u[i]`` and ``len(u)``; scalar spaces convert directly."""
+
+    def __init__(self, space, number):
+        self.space, self.number = space, number
+        self._args = [_ufl.Arg(space, k, number) for k in range(space.n_comp)]
+
+    def __getitem__(self, i):
+        return self._args[i]
+
+    def __len__(self):
+        return self.space.n_comp
+
+    def __iter__(self):
+        return iter(self._args)
+
+    def ufl_expr(self):
+        if self.space.n_comp != 1:
+            raise TypeError("a mixed trial/test function must be indexed")
+        return self._args[0]
+
+
+for _op in ("__add__", "__radd__", "__sub__", "__rsub__", "__mul__", "__rmul__", "__truediv__", "__rtruediv__", "__neg__", "__pow__"):
+    def _mk(op):
+        def f(self, *a):
+            return getattr(self.ufl_expr(), op)(*a)
+        return f
+    setattr(_Indexable, _op, _mk(_op))
+
+
+def TrialFunction(space):
+    return _Indexable(space, 1)
+
+
+def TestFunction(space):
+    return _Indexable(space, 0)
+
+
+def TestFunctions(space):
+    return tuple(_ufl.Arg(space, k, 0) for k in range(space.n_comp))
+
+
+def TrialFunctions(space):
+    return tuple(_ufl.Arg(space, k, 1) for k in range(space.n_comp))
+
+
+# ---- vectors and functions --------------------------------------------------------------------------------------------
+class GenericVector:
+    """dolfin GenericVector look-alike over a backend storage (numpy array or CUDA tensor)."""
+
+    def __init__(self, store, n_comp=1, function=None):
+        self.store, self.n_comp, self.function = store, n_comp, function
+
+    def __getitem__(self, key):
+        return self.store.numpy()[key]
+
+    def __setitem__(self, key, value):
+        if isinstance(key, slice) and key == slice(None):
+            arr = np.broadcast_to(np.asarray(value, dtype=np.float64), (self.store.size(),))
+            self.store.set_numpy(np.ascontiguousarray(arr))
+        else:
+            a = self.store.numpy()
+            a[key] = value
+            self.store.set_numpy(a)
+
+    def get_local(self):
+        return self.store.numpy()
+
+    def set_local(self, values):
+        self[:] = values
+
+    def apply(self, mode=""):
+        pass
+
+    def update_ghost_values(self):
+        self.store.update_ghosts(self.n_comp)
+
+    def size(self):
+        return self.store.size()
+
+    def norm(self, kind="l2"):
+        return self.store.norm2()
+
+    def copy(self):
+        return GenericVector(self.store.clone(), self.n_comp)
+
+    def _binary(self, other, sign):
+        out = self.store.clone()
+        if isinstance(other, GenericVector):
+            out.axpy(sign, other.store)
+        else:
+            out.add_scalar(sign * float(other))
+        return GenericVector(out, self.n_comp)
+
+    def __add__(self, o):
+        return self._binary(o, 1.0)
+
+    __radd__ = __add__
+
+    def __sub__(self, o):
+        return self._binary(o, -1.0)
+
+    def __mul__(self, c):
+        out = self.store.clone()
+        out.scale(float(c))
+        return GenericVector(out, self.n_comp)
+
+    __rmul__ = __mul__
+
+    def __truediv__(self, c):
+        return self * (1.0 / float(c))
+
+    def zero(self):
+        self[:] = 0.0
+
+
+class Function:
+    _count = 0
+
+    def __new__(cls, space, *args):
+        sp = space.space if isinstance(space, Function) else space
+        if cls is Function and sp.n_comp > 1:
+            return object.__new__(_MixedFunction)
+        return object.__new__(cls)
+
+    def __init__(self, space, *args):
+        if isinstance(space, Function):                 # Function(f): copy
+            other = space
+            space = other.space
+            self._init(space)
+            self.assign(other)
+            return
+        self._init(space)
+
+    def _init(self, space):
+        self.space = space
+        Function._count += 1
+        self._name = f"f_{Function._count}"
+        self._vec = GenericVector(get_backend().zeros(space.dim(), space), space.n_comp, self)
+
+    # dolfin API
+    def vector(self):
+        return self._vec
+
+    def function_space(self):
+        return self.space
+
+    def ufl_function_space(self):
+        return self.space
+
+    def rename(self, name, label):
+        self._name = name
+
+    def name(self):
+        return self._name
+
+    def copy(self, deepcopy=True):
+        return Function(self)
+
+    def assign(self, other):
+        if isinstance(other, Function):
+            self._vec.store.copy_from(other._vec.store)
+        elif isinstance(other, (Constant, Expression)):
+            self._vec[:] = interpolate(other, self.space)._vec[:]
+        else:
+            raise TypeError("Function.assign: expected a Function, Constant or Expression")
+
+    def compute_vertex_values(self, mesh=None):
+        a = self._vec.get_local()
+        return a.reshape(-1, self.space.n_comp).T.ravel() if self.space.n_comp > 1 else a
+
+    # UFL behaviour
+    def ufl_expr(self):
+        if self.space.vector:
+            return _ufl.Vec(_ufl.Field(self, 0), _ufl.Field(self, 1))
+        if self.space.n_comp != 1:
+            raise TypeError("a mixed Function must be indexed")
+        return _ufl.Field(self, 0)
+
+
+class _MixedFunction(Function):
+    """Functions on mixed / vector spaces are indexable; scalar ones must not look like sequences to numpy (FEDM builds
+    object arrays of coefficient functions, fedm/functions.py:839-841)."""
+
+    def __getitem__(self, i):
+        if i < 0:
+            i += self.space.n_comp
+        if not 0 <= i < self.space.n_comp:
+            raise IndexError(i)
+        return _ufl.Field(self, i)
+
+    def __len__(self):
+        return self.space.n_comp
+
+
+class FunctionAssigner:
+    """``FunctionAssigner(receiving, assigning)`` between a mixed space and a list of scalar spaces (either direction)."""
+
+    def __init__(self, receiving, assigning):
+        self.to_list = isinstance(receiving, (list, tuple))
+
+    def assign(self, receiving, assigning):
+        if self.to_list:                                    # per-field functions <- mixed function
+            n = assigning.space.n_comp
+            nv = assigning.space.mesh().num_vertices()
+            for k, f in enumerate(receiving):
+                f.vector().store.strided_copy_from(assigning.vector().store, n, k, 1, 0, nv)
+        else:                                               # mixed function <- per-field functions
+            n = receiving.space.n_comp
+            nv = receiving.space.mesh().num_vertices()
+            for k, f in enumerate(assigning):
+                receiving.vector().store.strided_copy_from(f.vector().store, 1, 0, n, k, nv)
+
+
+def _forward_ops(cls):
+    for op in ("__add__", "__radd__", "__sub__", "__rsub__", "__mul__", "__rmul__", "__truediv__", "__rtruediv__", "__neg__",
+               "__pow__", "__rpow__", "__abs__"):
+        def mk(op):
+            def f(self, *a):
+                return getattr(self.ufl_expr(), op)(*a)
+            return f
+        setattr(cls, op, mk(op))
+
+
+_forward_ops(Function)
+_forward_ops(_MixedFunction)
+
+
+class Constant:
+    def __init__(self, value, cell=None):
+        if isinstance(value, (tuple, list)):
+            self.values = [float(v) for v in value]
+        else:
+            self.values = [float(value)]
+        self._node = None
+
+    def assign(self, value):
+        self.values = [float(value)] if not isinstance(value, Constant) else list(value.values)
+
+    def __float__(self):
+        return self.values[0]
+
+    def ufl_expr(self):
+        if len(self.values) == 2:
+            return _ufl.Vec(_ufl.Param(lambda: self.values[0], "c0"), _ufl.Param(lambda: self.values[1], "c1"))
+        if self._node is None:
+            self._node = _ufl.Param(lambda: self.values[0], "const")
+        return self._node
+
+
+_forward_ops(Constant)
+
+
+class Expression:
+    """``Expression(cpp_string, degree=..., **user_parameters)``; the user parameters stay mutable attributes."""
+
+    def __init__(self, cpp_code, degree=None, element=None, **params):
+        object.__setattr__(self, "_params", dict(params))
+        object.__setattr__(self, "cpp_code", cpp_code)
+        object.__setattr__(self, "degree", 0 if degree is None else degree)
+        object.__setattr__(self, "_ast", cexpr.parse(cpp_code))
+        object.__setattr__(self, "_node", None)
+
+    def __getattr__(self, name):
+        params = object.__getattribute__(self, "_params")
+        if name in params:
+            return params[name]
+        raise AttributeError(name)
+
+    def __setattr__(self, name, value):
+        if name in self._params or not name.startswith("_"):
+            self._params[name] = value
+        else:
+            object.__setattr__(self, name, value)
+
+    def _scalar_params(self):
+        return {k: (float(v) if not isinstance(v, Function) else v) for k, v in self._params.items() if not callable(v) or isinstance(v, Function)}
+
+    def value_at(self, x0, x1, nodal=None):
+        """numpy evaluation at points; Function-valued parameters are taken at the same nodes (``nodal`` = vertex ids)."""
+        p = {}
+        for k, v in self._params.items():
+            if isinstance(v, Function):
+                vals = v.vector().get_local()
+                p[k] = vals if nodal is None else vals[nodal]
+            elif isinstance(v, (int, float, np.floating, np.integer)):
+                p[k] = float(v)
+        return cexpr.evaluate(self._ast, (x0, x1), p)
+
+    def __float__(self):
+        return float(self.value_at(0.0, 0.0))
+
+    def ufl_expr(self):
+        if self._node is not None:
+            return self._node
+        if self.degree == 0:
+            node = _ufl.Param(lambda: float(self.value_at(0.0, 0.0)), self.cpp_code)
+        elif self._ast == ("x", 0):
+            node = _ufl.Coord(0)
+        elif self._ast == ("x", 1):
+            node = _ufl.Coord(1)
+        else:
+            pmap = {k: _ufl.Param((lambda k=k: float(self._params[k])), k) for k, v in self._params.items()
+                    if isinstance(v, (int, float, np.floating, np.integer))}
+            node = _ufl.Interp(cexpr.to_ufl(self._ast, pmap, _ufl), self.degree)
+        object.__setattr__(self, "_node", node)
+        return node
+
+
+_forward_ops(Expression)
+
+
+def interpolate(v, space):
+    f = Function(space)
+    xy = space.mesh().coordinates()
+    n = xy.shape[0]
+    if isinstance(v, Function):
+        f.assign(v)
+    elif isinstance(v, Constant):
+        f.vector()[:] = np.tile(np.asarray(v.values), n) if space.n_comp > 1 else v.values[0]
+    elif isinstance(v, Expression):
+        vals = np.broadcast_to(np.asarray(v.value_at(xy[:, 0], xy[:, 1], nodal=np.arange(n)), dtype=np.float64), (n,))
+        f.vector()[:] = np.ascontiguousarray(vals)
+    else:
+        raise TypeError("interpolate: expected an Expression, Constant or Function")
+    return f
+
+
+# ---- boundary conditions ----------------------------------------------------------------------------------------------
+class DirichletBC:
+    def __init__(self, space, value, where, method="topological"):
+        if isinstance(space, _SubSpace):
+            self.space, self.comp = space.parent, space.comp
+        else:
+            self.space, self.comp = space, 0
+        self.value = value
+        tri = self.space.mesh().tri
+        fv = tri.exterior_facets()
+        xy = tri.coords
+        inside = where.inside if isinstance(where, SubDomain) else where
+        nodes = set()
+        for a, b in fv:
+            pa, pb = xy[a], xy[b]
+            if inside(pa, True) and inside(pb, True) and inside(0.5 * (pa + pb), True):
+                nodes.add(int(a))
+                nodes.add(int(b))
+        self.nodes = np.array(sorted(nodes), dtype=np.int32)
+
+    def current_value(self):
+        v = self.value
+        if isinstance(v, Constant):
+            return v.values[0]
+        if isinstance(v, Expression):
+            return float(v)
+        return float(v)
+
+    def apply(self, *tensors):
+        for t in tensors:
+            if isinstance(t, (_LazyMatrix, _LazyVector)):
+                t.bcs.append(self)
+            # apply(b, x) inside FEDM's Problem.F is a no-op here: the device Newton applies the conditions itself
+
+
+# ---- assemble / solve ---------------------------------------------------------------------------------------------------
+class _LazyMatrix:
+    def __init__(self, form):
+        self.form, self.bcs = form, []
+
+    def ident_zeros(self):
+        pass
+
+
+class _LazyVector(GenericVector):
+    def __init__(self, form):
+        self.form, self.bcs = form, []
+
+
+def assemble(form, tensor=None, keep_diagonal=False):
+    """Forms are assembled where they are consumed (``solve`` / the nonlinear solver); this records the form."""
+    if isinstance(form, _ufl.Jacobian):
+        return _LazyMatrix(form)
+    has_trial = any(_ufl._has_trial(i.integrand) for i in form.integrals)
+    return _LazyMatrix(form) if has_trial else _LazyVector(form)
+
+
+def _quadrature_degree():
+    q = parameters["form_compiler"].get("quadrature_degree", None)
+    return None if q in (None, -1, "auto") else int(q)
+
+
+def _solve_linear(a_form, L_form, u, bcs, tight=True):
+    residual = action(a_form, u) - L_form
+    prob = get_backend().compile(residual, u, bcs, _quadrature_degree())
+    prob.solve_newton(u, rtol=1e-12, atol=0.0, max_it=3, linear_solver="mumps", raise_on_failure=False)
+
+
+def solve(A, x, b, *args):
+    if not isinstance(A, _LazyMatrix) or not isinstance(b, _LazyVector):
+        raise NotImplementedError("solve(A, x, b): A and b must come from assemble()")
+    u = x.function
+    if u is None:
+        raise NotImplementedError("solve(A, x, b): x must be the vector of a Function")
+    bcs = list({id(bc): bc for bc in A.bcs + b.bcs}.values())
+    _solve_linear(A.form, b.form, u, bcs)
+
+
+def project(expr, V=None, solver_type="lu", **kw):
+    expr = _ufl.as_expr(expr)
+    if V is None:
+        mesh = _find_mesh(expr)
+        V = FunctionSpace(mesh, "P", 1)
+    if V.n_comp != 1:
+        raise NotImplementedError("project onto mixed/vector spaces")
+    u, v = TrialFunction(V), TestFunction(V)
+    out = Function(V)
+    _solve_linear((u * v) * dx, (expr * v) * dx, out, [])
+    return out
+
+
+def _find_mesh(e):
+    if isinstance(e, _ufl.Vec):
+        return _find_mesh(e.x) or _find_mesh(e.y)
+    if isinstance(e, _ufl.Field):
+        return e.fn.space.mesh()
+    if isinstance(e, _ufl.Arg):
+        return e.space.mesh()
+    for c in e.children():
+        m = _find_mesh(c)
+        if m is not None:
+            return m
+    return None
+
+
+class NonlinearProblem:
+    def __init__(self):
+        pass
+
+    def F(self, b, x):
+        raise NotImplementedError
+
+    def J(self, A, x):
+        raise NotImplementedError
+
+
+class PETScSNESSolver:
+    """Newton solver with dolfin's parameter names.  ``solve(problem, x)`` reads ``problem.linear_form``,
+    ``problem.bilinear_form`` and ``problem.bcs`` (what FEDM's ``Problem`` stores, fedm/functions.py:182-186), compiles the
+    residual form once and runs the whole Newton-Krylov iteration in the backend; it returns (iterations, converged) and
+    raises RuntimeError on non-convergence, as dolfin does with error_on_nonconvergence=True."""
+
+    def __init__(self, *args):
+        self.parameters = _Params({"relative_tolerance": 1e-9, "absolute_tolerance": 1e-10, "solution_tolerance": 1e-16,
+                                   "maximum_iterations": 50, "linear_solver": "default", "preconditioner": "default",
+                                   "error_on_nonconvergence": True, "report": True, "method": "default", "line_search": "basic",
+                                   "maximum_residual_evaluations": 2000, "sign": "default"})
+        self._compiled = {}
+        self.last = None
+
+    def solve(self, problem, x):
+        F = getattr(problem, "linear_form", None)
+        if F is None:
+            raise NotImplementedError("PETScSNESSolver.solve: the problem must expose .linear_form/.bcs (FEDM's Problem class)")
+        u = x.function
+        key = id(problem)
+        if key not in self._compiled:
+            self._compiled[key] = get_backend().compile(F, u, list(getattr(problem, "bcs", [])), _quadrature_degree())
+        prob = self._compiled[key]
+        p = self.parameters
+        res = prob.solve_newton(u, rtol=p["relative_tolerance"], atol=p["absolute_tolerance"], stol=p["solution_tolerance"],
+                                max_it=p["maximum_iterations"], linear_solver=p["linear_solver"],
+                                raise_on_failure=bool(p["error_on_nonconvergence"]))
+        self.last = res
+        return res
+
+
+class NonlinearVariationalSolver:
+    pass
+
+
+# ---- norms ------------------------------------------------------------------------------------------------------------
+def _mass_apply(space, vals):
+    tri = space.mesh().tri
+    p = tri.coords[tri.cells]
+    det = np.abs((p[:, 1, 0] - p[:, 0, 0]) * (p[:, 2, 1] - p[:, 0, 1]) - (p[:, 2, 0] - p[:, 0, 0]) * (p[:, 1, 1] - p[:, 0, 1]))
+    loc = vals[tri.cells]
+    s = loc.sum(axis=1)
+    out = np.zeros_like(vals)
+    for a in range(3):
+        np.add.at(out, tri.cells[:, a], det * (loc[:, a] + s) / 24.0)
+    return out
+
+
+def norm(v, norm_type="l2", mesh=None):
+    if isinstance(v, GenericVector):
+        return v.norm("l2")
+    if isinstance(v, Function):
+        if norm_type.lower() != "l2":
+            raise NotImplementedError(norm_type)
+        a = v.vector().get_local()
+        return float(np.sqrt(a @ _mass_apply(v.space, a)))
+    raise TypeError("norm: expected a vector or a Function")
+
+
+def errornorm(u, uh, norm_type="l2", **kw):
+    e = u.vector().get_local() - uh.vector().get_local()
+    return float(np.sqrt(e @ _mass_apply(u.space, e)))
+
+
+# ---- output -------------------------------------------------------------------------------------------------------------
+class File:
+    """PVD/VTU writer (ASCII, vertex values) -- enough for FEDM's ``file_output`` and for its tests, which read
+    ``<name>000000.vtu``."""
+
+    def __init__(self, path, *args):
+        self.path = Path(str(path))
+        self.count = 0
+        self.entries = []
+
+    def write(self, obj, t=0.0):
+        self.path.parent.mkdir(parents=True, exist_ok=True)      # dolfin creates the output folder on first write
+        if isinstance(obj, Function):
+            self << (obj, t)
+        return self
+
+    def __lshift__(self, obj):
+        t = 0.0
+        if isinstance(obj, tuple):
+            obj, t = obj
+        self.path.parent.mkdir(parents=True, exist_ok=True)
+        if not isinstance(obj, Function):
+            return self                           # meshes and mesh functions: not needed downstream
+        stem = self.path.stem
+        vtu = self.path.parent / f"{stem}{self.count:06d}.vtu"
+        tri = obj.space.mesh().tri
+        vals = obj.vector().get_local()
+        with open(vtu, "w") as fh:
+            fh.write('<?xml version="1.0"?>\n<VTKFile type="UnstructuredGrid"  version="0.1"  >\n<UnstructuredGrid>\n')
+            fh.write(f'<Piece  NumberOfPoints="{tri.num_vertices}" NumberOfCells="{tri.num_cells}">\n<Points>\n')
+            fh.write('<DataArray  type="Float64"  NumberOfComponents="3"  format="ascii">')
+            fh.write("  ".join(f"{x!r} {y!r} 0" for x, y in tri.coords.tolist()))
+            fh.write('</DataArray>\n</Points>\n<Cells>\n<DataArray  type="UInt32"  Name="connectivity"  format="ascii">')
+            fh.write("  ".join(f"{a} {b} {c}" for a, b, c in tri.cells.tolist()))
+            fh.write('</DataArray>\n<DataArray  type="UInt32"  Name="offsets"  format="ascii">')
+            fh.write(" ".join(str(3 * (i + 1)) for i in range(tri.num_cells)))
+            fh.write('</DataArray>\n<DataArray  type="UInt8"  Name="types"  format="ascii">')
+            fh.write(" ".join("5" for _ in range(tri.num_cells)))
+            fh.write(f'</DataArray>\n</Cells>\n<PointData  Scalars="{obj.name()}"> \n')
+            fh.write(f'<DataArray  type="Float64"  Name="{obj.name()}"  format="ascii">')
+            fh.write("  ".join(repr(float(v)) for v in vals))
+            fh.write('</DataArray> \n</PointData> \n</Piece>\n</UnstructuredGrid>\n</VTKFile>')
+        self.entries.append((t, vtu.name))
+        self.count += 1
+        with open(self.path, "w") as fh:
+            fh.write('<?xml version="1.0"?>\n<VTKFile type="Collection" version="0.1">\n<Collection>\n')
+            for tt, name in self.entries:
+                fh.write(f'<DataSet timestep="{tt!r}" part="0" file="{name}" />\n')
+            fh.write("</Collection>\n</VTKFile>\n")
+        return self
+
+
+class XDMFFile:
+    """Checkpoint writer.  No HDF5 library is available in this environment, so checkpoints go to ``<name>.npz``
+    (arrays ``<name>_<k>`` in vertex order plus their times)."""
+
+    class Encoding:
+        HDF5 = "HDF5"
+        ASCII = "ASCII"
+
+    def __init__(self, *args):
+        self.path = Path(str(args[-1]))
+        self.parameters = _Params()
+        self.data = {}
+
+    def write_checkpoint(self, f, name, t=0.0, encoding=None, append=False):
+        k = sum(1 for key in self.data if key.startswith(name + "_") and not key.endswith("_t"))
+        self.data[f"{name}_{k}"] = f.vector().get_local()
+        self.data[f"{name}_{k}_t"] = np.array(t)
+        self.path.parent.mkdir(parents=True, exist_ok=True)
+        np.savez(self.path.with_suffix(".npz"), **self.data)
+
+    def write(self, *args):
+        pass
+
+    def close(self):
+        pass

@@ -35,6 +35,8 @@ SIGNATURES = {
     "fedmx_matrix_get_bsr": (C.c_int, [C.c_void_p, C.c_void_p]),
     "fedmx_dirichlet_set": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
     "fedmx_model_set": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "fedmx_plugin_load": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "fedmx_plugin_set_field": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]),
     "fedmx_fields_bind": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "fedmx_assemble_residual": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_void_p,
                                           C.c_int, C.c_void_p]),

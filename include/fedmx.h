@@ -41,7 +41,8 @@ enum {
     FEDMX_MODEL_TOF = 2,        /* tests/integrated_tests/time_of_flight/fedm_tof.py:120-127 */
     FEDMX_MODEL_GLOW = 3,       /* tests/integrated_tests/glow_discharge/fedm_gd.py:349-385 */
     FEDMX_MODEL_POISSON = 4,    /* weak_form_Poisson_equation alone (initial potential), fedm_streamer.py:210-223 */
-    FEDMX_MODEL_PROJECTION = 5  /* dolfin project() onto P1: fedm_tof.py:165, fedm_gd.py:309,432 */
+    FEDMX_MODEL_PROJECTION = 5, /* dolfin project() onto P1: fedm_tof.py:165, fedm_gd.py:309,432 */
+    FEDMX_MODEL_PLUGIN = 100    /* row kernel generated from a UFL-lite form at run time (fedmx_plugin_load) */
 };
 
 /* SNES convergence reasons (subset of PETSc's SNESConvergedReason the reference can observe) */
@@ -92,6 +93,15 @@ int fedmx_dirichlet_set(fedmx_ctx *ctx, int comp, int64_t n_nodes, const int32_t
  * (fedm_streamer.py:296-297): selects the hand-written cell/facet kernel family and its constants.
  * h_params: model-specific double array (see fedm_b200/models.py for the layouts). */
 int fedmx_model_set(fedmx_ctx *ctx, int model_id, int n_params, const double *h_params);
+/* Run-time compiled forms -- the role of FFC + dijitso for `F = action(F,u_new); J = derivative(F,u_new,u)` with arbitrary
+ * user forms (fedm_streamer.py:296-297): fedm_b200/formcompiler.py lowers a UFL-lite form to CUDA source for the generic
+ * row kernel (fedm_b200/csrc/row_kernel.cuh), nvcc builds a plug-in .so, fedmx_plugin_load binds it to the context and
+ * fedmx_plugin_set_field tells the kernel where coefficient k lives (component `offset` of a node-interleaved device
+ * vector with `stride` components).  Scalar parameters (dt, dt_old, Constants ...) go through fedmx_model_set(
+ * FEDMX_MODEL_PLUGIN, n, values) before every solve. */
+int fedmx_plugin_load(fedmx_ctx *ctx, const char *so_path);
+int fedmx_plugin_set_field(fedmx_ctx *ctx, int k, const double *d_ptr, int stride, int offset);
+
 /* Per-node coefficient fields (P1 Functions: history terms, transport/rate coefficients...),
  * d_fields[n_vertices][n_fields], caller-owned. */
 int fedmx_fields_bind(fedmx_ctx *ctx, int n_fields, const double *d_fields);

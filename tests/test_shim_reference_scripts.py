@@ -1,0 +1,71 @@
+"""The reference's UNMODIFIED ``fedm`` package and UNMODIFIED integrated-test scripts executed on this repo's dolfin shim
+(``compat/dolfin`` -> ``fedm_b200.dolfin`` + UFL-lite) with the oracle's numpy backend, compared with the reference's goldens.
+This validates the shim semantics (form capture, UFL degree estimation, Expression interpolation, project, assigners,
+boundary conditions, file_output) on the CPU; the same shim drives the CUDA backend on the GPU box
+(tests/test_gpu_shim.py).  Needs /root/reference (present in the build container only) -- skipped elsewhere."""
+import importlib
+import os
+import re
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+REF = Path("/root/reference")
+ROOT = Path(__file__).resolve().parent.parent
+pytestmark = pytest.mark.skipif(not (REF / "fedm" / "functions.py").exists(), reason="reference checkout not available")
+
+
+@pytest.fixture()
+def shim_env(monkeypatch):
+    for p in (str(REF), str(ROOT / "compat")):
+        monkeypatch.syspath_prepend(p)
+    for name in [m for m in sys.modules if m == "dolfin" or m == "fedm" or m.startswith("fedm.")]:
+        monkeypatch.delitem(sys.modules, name)
+    import dolfin
+    from oracle.ufl_backend import NumpyBackend
+    dolfin.set_backend(NumpyBackend())
+    yield dolfin
+    dolfin.set_backend(None)
+    for name in [m for m in sys.modules if m == "dolfin" or m == "fedm" or m.startswith("fedm.")]:
+        sys.modules.pop(name, None)
+
+
+def _run(script_dir, module, **kw):
+    sys.path.insert(0, str(script_dir))
+    try:
+        sys.modules.pop(module, None)
+        mod = importlib.import_module(module)
+        mod.main(**kw)
+    finally:
+        sys.path.remove(str(script_dir))
+        sys.modules.pop(module, None)
+
+
+def test_reference_time_of_flight_script_unmodified(shim_env, tmp_path, golden_dir, capsys):
+    _run(REF / "tests/integrated_tests/time_of_flight", "fedm_tof", output_dir=tmp_path)
+    rel = float((tmp_path / "relative error.log").read_text().split("=")[-1])
+    ref = float((golden_dir / "time_of_flight_relative_error.log").read_text().split("=")[-1])
+    assert abs(rel - ref) <= 1e-10 * ref
+    text = (tmp_path / "number density" / "electrons" / "electrons000000.vtu").read_text()
+    vals = np.array(re.search(r"<PointData.*?<DataArray[^>]*>(.*?)</DataArray>", text, re.S).group(1).split(), dtype=float)
+    gold = np.load(golden_dir / "tof_electrons_f3199.npy")
+    assert np.abs(vals - gold).max() <= 1e-11 * gold.max()
+
+
+@pytest.mark.skipif(not os.environ.get("FEDM_B200_SLOW"), reason="4 minutes; set FEDM_B200_SLOW=1")
+def test_reference_glow_discharge_script_unmodified(shim_env, tmp_path, golden_dir):
+    _run(REF / "tests/integrated_tests/glow_discharge", "fedm_gd",
+         input_dir=REF / "tests/integrated_tests/glow_discharge/file_input", output_dir=tmp_path)
+    rows = [[float(t) for t in ln.split()] for ln in (tmp_path / "relative error.log").read_text().splitlines()]
+    gold = [[float(t) for t in ln.split()] for ln in (golden_dir / "glow_discharge_relative_error.log").read_text().splitlines()]
+    assert len(rows) == 6
+    for r, g in zip(rows, gold):
+        assert abs(r[0] - g[0]) <= 1e-10 * g[0] and abs(r[2] - g[2]) <= 1e-10 * g[2]
+    g = np.load(golden_dir / "glow_h5.npz")
+    d2v = np.empty(20201, dtype=np.int64)
+    d2v[g["cell_dofs"]] = g["topology"].ravel()
+    for name in ("electrons", "Ar_plus", "Ar_star"):
+        z = np.load(tmp_path / "number density" / name / f"{name}.npz")
+        assert np.abs((z[f"{name}_1"][d2v] - g[name + "_1"]) / g[name + "_1"]).max() <= 1e-11
