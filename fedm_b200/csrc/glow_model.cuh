@@ -19,63 +19,7 @@
 //   [80+r] energy loss of reaction r, [88+r] 1 if reaction r is 'Umean'-dependent (semi-implicit)
 #pragma once
 
-template <int N>
-struct Dual {
-    double v;
-    double d[N];
-};
-
-template <int N> __device__ __forceinline__ Dual<N> dconst(double c) {
-    Dual<N> r; r.v = c;
-#pragma unroll
-    for (int i = 0; i < N; ++i) r.d[i] = 0.0;
-    return r;
-}
-template <int N> __device__ __forceinline__ Dual<N> operator+(const Dual<N> &a, const Dual<N> &b) {
-    Dual<N> r; r.v = a.v + b.v;
-#pragma unroll
-    for (int i = 0; i < N; ++i) r.d[i] = a.d[i] + b.d[i];
-    return r;
-}
-template <int N> __device__ __forceinline__ Dual<N> operator-(const Dual<N> &a, const Dual<N> &b) {
-    Dual<N> r; r.v = a.v - b.v;
-#pragma unroll
-    for (int i = 0; i < N; ++i) r.d[i] = a.d[i] - b.d[i];
-    return r;
-}
-template <int N> __device__ __forceinline__ Dual<N> operator-(const Dual<N> &a) {
-    Dual<N> r; r.v = -a.v;
-#pragma unroll
-    for (int i = 0; i < N; ++i) r.d[i] = -a.d[i];
-    return r;
-}
-template <int N> __device__ __forceinline__ Dual<N> operator*(const Dual<N> &a, const Dual<N> &b) {
-    Dual<N> r; r.v = a.v * b.v;
-#pragma unroll
-    for (int i = 0; i < N; ++i) r.d[i] = a.d[i] * b.v + a.v * b.d[i];
-    return r;
-}
-template <int N> __device__ __forceinline__ Dual<N> operator*(const Dual<N> &a, double c) {
-    Dual<N> r; r.v = a.v * c;
-#pragma unroll
-    for (int i = 0; i < N; ++i) r.d[i] = a.d[i] * c;
-    return r;
-}
-template <int N> __device__ __forceinline__ Dual<N> operator*(double c, const Dual<N> &a) { return a * c; }
-template <int N> __device__ __forceinline__ Dual<N> operator+(const Dual<N> &a, double c) { Dual<N> r = a; r.v += c; return r; }
-template <int N> __device__ __forceinline__ Dual<N> operator+(double c, const Dual<N> &a) { return a + c; }
-template <int N> __device__ __forceinline__ Dual<N> operator-(const Dual<N> &a, double c) { Dual<N> r = a; r.v -= c; return r; }
-template <int N> __device__ __forceinline__ Dual<N> dexp(const Dual<N> &a) {
-    Dual<N> r; r.v = exp(a.v);
-#pragma unroll
-    for (int i = 0; i < N; ++i) r.d[i] = r.v * a.d[i];
-    return r;
-}
-// |x| with derivative sign(x) (0 at 0), as UFL differentiates abs()
-template <int N> __device__ __forceinline__ Dual<N> dabs(const Dual<N> &a) {
-    const double s = (a.v > 0.0) ? 1.0 : ((a.v < 0.0) ? -1.0 : 0.0);
-    return a * s;
-}
+#include "dual.cuh"
 
 struct GlowModel {
     static constexpr int MINB = 2, MINB_RES = 2;

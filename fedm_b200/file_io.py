@@ -10,7 +10,7 @@ from pathlib import Path
 
 import numpy as np
 
-from .utils import comma_separated, print_rank_0
+from .utils import comma_separated, mesh_info, print_rank_0
 
 
 class Files:
@@ -259,3 +259,96 @@ def print_time_step(dt):
 
 def print_time(t):
     print_rank_0("t =", t)
+
+
+# ---- output (thin: PVD/VTU through the shim's File, checkpoints through its XDMFFile stand-in) -----------------------------
+def truncate_file(path):
+    path = Path(path)
+    path.parent.mkdir(parents=True, exist_ok=True)
+    path.write_text("")
+
+
+def output_files(file_type, type_of_output, output_file_names):
+    """One PVD or XDMF output object per name under ``files.output_folder_path/<type_of_output>/<name>/``."""
+    from . import dolfin as df
+    makers = {"pvd": df.File, "xdmf": df.XDMFFile}
+    if file_type not in makers:
+        raise ValueError(f"fedm.output_files: file type '{file_type}' is not valid. Options are 'pvd' or 'xdmf'.")
+    folder = files.output_folder_path / type_of_output
+    out = []
+    for name in output_file_names:
+        handle = makers[file_type](str(folder / name / f"{name}.{file_type}"))
+        if file_type == "xdmf":
+            handle.parameters["flush_output"] = True
+        out.append(handle)
+    return out
+
+
+def file_output(t, t_old, t_out, step, t_out_list, step_list, file_type, output_file_list, particle_name, u_old, u_old1, unit="s"):
+    """Writes every output instant t_out <= t, linearly interpolated between the two last time levels, and advances the
+    output clock through the (t_out_list, step_list) schedule.  Returns (next t_out, current step)."""
+    from . import dolfin as df
+    scales = {"ns": 1e9, "us": 1e6, "ms": 1e3, "s": 1.0}
+    if unit not in scales:
+        raise ValueError(f"fedm.file_output: unit '{unit}' not valid. Options are {comma_separated(list(scales))}.'")
+    scale = scales[unit]
+    index = len(t_out_list) - 1 if t > max(t_out_list) else next(i for i, val in enumerate(t_out_list) if val > t)
+    while t_out <= t:
+        for i, handle in enumerate(output_file_list):
+            snap = df.Function(u_old1[i].function_space())
+            snap.vector()[:] = u_old1[i].vector()[:] + (t_out - t_old) * (u_old[i].vector()[:] - u_old1[i].vector()[:]) / (t - t_old)
+            if file_type[i] == "pvd":
+                snap.rename(particle_name[i], str(i))
+                handle << (snap, t_out * scale)
+            elif file_type[i] == "xdmf":
+                handle.write_checkpoint(snap, particle_name[i], t_out * scale, df.XDMFFile.Encoding.HDF5, True)
+            else:
+                raise ValueError(f"fedm.file_output: file type '{file_type}' not recognised. Options are 'pvd' and 'xdmf'.")
+        if 0.999 * t_out_list[index - 1] <= t_out < 0.999 * t_out_list[index]:
+            step = step_list[index - 1]
+        elif t_out >= 0.999 * t_out_list[index]:
+            step = step_list[index]
+        t_out += step
+    return t_out, step
+
+
+def mesh_statistics(mesh):
+    from . import dolfin as df
+    folder = files.output_folder_path / "mesh"
+    df.File(str(folder / "mesh.pvd")).write(mesh)
+    text = mesh_info(mesh)
+    print_rank_0(text.rstrip())
+    if df.MPI.rank(df.MPI.comm_world) == 0:
+        (folder / "mesh info.txt").write_text(text)
+
+
+def numpy_2d_array_to_str(x):
+    body = str(np.asarray(x)).replace("[", "").replace("]", "")
+    return "\n".join(line.strip() for line in body.split("\n"))
+
+
+def log(log_type, log_file_name, *args):
+    """Appends a block to model.log: 'properties', 'conditions', 'matrices', 'initial time', 'time', 'mesh'."""
+    from . import dolfin as df
+    if df.MPI.rank(df.MPI.comm_world) != 0:
+        return
+    kinds = ["properties", "conditions", "matrices", "initial time", "time", "mesh"]
+    if log_type not in kinds:
+        raise ValueError(f"fedm.log: log_type '{log_type}' not valid. Options are {comma_separated(kinds)}.")
+    with open(log_file_name, "a") as fh:
+        if log_type == "properties":
+            gas, model, names, masses, charges = args
+            fh.write(f"Gas:\t{gas}\n\nmodel:\t{model}\n\nParticle names: \n{names}\n\nMass:\n{masses}\n\nCharge:\n{charges}\n\n")
+        elif log_type == "conditions":
+            dt_var, U_w, p0, gap, N0, Tgas = args
+            fh.write(f"Simulation conditions:\ndt = {dt_var} s\tU_w = {U_w} V\tp_0 = {p0} Torr\td = {gap} m\tN_0 = {N0} m^-3\tT_gas = {Tgas} K\n\n")
+        elif log_type == "matrices":
+            gain, loss, power = args
+            fh.write("gain matrix:\n" + numpy_2d_array_to_str(gain) + "\n\nloss matrix:\n" + numpy_2d_array_to_str(loss) +
+                     "\n\npower matrix:\n" + numpy_2d_array_to_str(power) + "\n\n")
+        elif log_type == "initial time":
+            fh.write(f"Time:\n{args[0]}\n")
+        elif log_type == "time":
+            fh.write(f"{args[0]}\n")
+        else:
+            fh.write(mesh_info(args[0]) + "\n")

@@ -15,3 +15,10 @@ def print_rank_0(*args, **kwargs):
 def comma_separated(items):
     """'a', 'b', 'c' -- used in the API's error messages."""
     return ", ".join(f"'{item}'" for item in items)
+
+
+def mesh_info(mesh):
+    """Element count and edge-length extremes (summed / reduced over processes in the reference)."""
+    return (f"Number of elements is: {int(mesh.num_cells())}\n"
+            f"Maximum element edge length is: {mesh.hmax():.5g}\n"
+            f"Minimum element edge length is: {mesh.hmin():.5g}")
