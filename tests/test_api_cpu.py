@@ -61,14 +61,14 @@ def test_readers_on_reference_decks(golden_dir):
         file_io.files.file_input = golden_dir / "does_not_exist"
 
 
-class _FakeVec:
-    def __init__(self, hot):
-        self.hot, self.t, self.n_comp = hot, None, 1
-
-
 class _FakeFn:
-    def __init__(self, hot):
-        self._v = _FakeVec(hot)
+    """Scalar function over the shim's GenericVector with the oracle's numpy store (no mesh needed)."""
+
+    def __init__(self, values):
+        from fedm_b200.dolfin import GenericVector
+        from oracle.ufl_backend import NumpyStore
+        self._v = GenericVector(NumpyStore(len(values)), 1, self)
+        self._v[:] = values
         self.assigned = 0
 
     def vector(self):
@@ -76,57 +76,56 @@ class _FakeFn:
 
     def assign(self, other):
         self.assigned += 1
-
-
-class _FakeHot:
-    n_owned = 10
-
-    def __init__(self, errors):
-        self.errors = list(errors)
-
-    def error_norm_strided(self, a, b, stride, offset, n, eps):
-        assert eps == 3.0e-16 and n == 10
-        return self.errors.pop(0)
+        self._v[:] = other.vector()[:]
 
 
 class _FakeSolver:
-    def __init__(self, fail_on):
-        self.calls, self.fail_on = 0, set(fail_on)
+    """Scripted solver: attempt k fails (raises like dolfin's SNES) or writes ``1 + delta_k`` into the solution."""
+
+    def __init__(self, fail_on, deltas):
+        self.calls, self.fail_on, self.deltas = 0, set(fail_on), list(deltas)
 
     def solve(self, problem, x):
         self.calls += 1
         if self.calls in self.fail_on:
             raise RuntimeError("Newton solver did not converge")
+        x[:] = 1.0 + self.deltas.pop(0)
         return 3, True
 
 
 class _Assigner:
-    def assign(self, a, b):
-        pass
+    def assign(self, receiving, assigning):
+        for f in receiving:
+            f.vector()[:] = assigning.vector()[:]
+
+
+def _estimate(delta, n=10):
+    new, old = np.full(n, 1.0 + delta), np.ones(n)
+    return float(np.linalg.norm(new - old + 3.0e-16) / np.linalg.norm(old + 3.0e-16))
 
 
 def test_adaptive_solver_accept_reject_and_log(tmp_path):
-    from fedm_b200.dolfin_shim import Expression
-    hot = _FakeHot([5e-3, 4e-4])                 # first attempt too inaccurate, third attempt accepted
-    solver = _FakeSolver(fail_on={2})            # second attempt: Newton failure
+    from fedm_b200.dolfin import Expression
+    e1, e2 = _estimate(5e-3), _estimate(4e-4)    # first attempt too inaccurate, third attempt accepted
+    solver = _FakeSolver(fail_on={2}, deltas=[5e-3, 4e-4])   # second attempt: Newton failure
     dt, dt_old = Expression("time_step", time_step=4e-12), Expression("time_step", time_step=1e30)
-    u_new, u_old = _FakeFn(hot), _FakeFn(hot)
-    new, old = [_FakeFn(hot), _FakeFn(hot), _FakeFn(hot)], [_FakeFn(hot), _FakeFn(hot), _FakeFn(hot)]
+    ones = np.ones(10)
+    u_new, u_old = _FakeFn(ones), _FakeFn(ones)
+    new, old = [_FakeFn(ones)], [_FakeFn(ones)]
     error, max_error = [0.0, 0.0], [1, 1, 1]
     log = tmp_path / "relative error.log"
 
     class P:
         t = 0.0
     t = F.adaptive_solver(solver, P(), 1e-9, dt, dt_old, u_new, u_old, new, old, _Assigner(), error, log, max_error, 1e-3, 1e-15,
-                          time_dependent_arguments=[], approximation="LFA")
-    dt1 = 4e-12 * (0.5 * 1e-3 / 5e-3)            # error >= ttol: dt *= 0.5*ttol/max_error
+                          time_dependent_arguments=[], approximation="LMEA")
+    dt1 = 4e-12 * (0.5 * 1e-3 / e1)              # error >= ttol: dt *= 0.5*ttol/max_error
     dt2 = dt1 * 0.5                              # exception: dt *= 0.5
     assert dt.time_step == dt2 and t == 1e-9 + dt2 and solver.calls == 3 and u_new.assigned == 2
     rows = log.read_text().splitlines(keepends=True)
-    assert rows == [f"{5e-3:<23}  {1e30:<23}  {4e-12:<23}\n", f"{4e-4:<23}  {1e30:<23}  {dt2:<23}\n"]
-    assert max_error[0] == 4e-4
+    assert rows == [f"{e1:<23}  {1e30:<23}  {4e-12:<23}\n", f"{e2:<23}  {1e30:<23}  {dt2:<23}\n"]
+    assert max_error[0] == e2
     # below dt_min the program terminates, as in the reference
-    hot2 = _FakeHot([1.0] * 50)
     with pytest.raises(SystemExit):
-        F.adaptive_solver(_FakeSolver(()), P(), 0.0, Expression("time_step", time_step=1e-14), dt_old, u_new, u_old, new, old,
-                          _Assigner(), [0.0], log, [1, 1, 1], 1e-3, 1e-15, approximation="LMEA")
+        F.adaptive_solver(_FakeSolver((), [1.0] * 50), P(), 0.0, Expression("time_step", time_step=1e-14), dt_old, u_new, u_old,
+                          new, old, _Assigner(), [0.0], log, [1, 1, 1], 1e-3, 1e-15, approximation="LMEA")

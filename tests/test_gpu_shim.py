@@ -21,8 +21,10 @@ def cuda_shim():
     sys.path[:0] = [str(ROOT / "compat"), str(ROOT / "examples")]
     import dolfin
     dolfin.set_backend(None)               # default backend = CUDA
+    dolfin.parameters["form_compiler"]["quadrature_degree"] = None   # scripts set this global; each test = a fresh process
     yield dolfin
     dolfin.set_backend(None)
+    dolfin.parameters["form_compiler"]["quadrature_degree"] = None
 
 
 def test_streamer_script_on_gpu_matches_oracle(cuda_shim, tmp_path, golden_dir):
