@@ -9,19 +9,27 @@
 // i.e. a block-diagonal two-stage (CPR-like) preconditioner.  PETSc's role here is PCApply inside KSPGMRES
 // (reference call site fedm/functions.py:1047); results do not depend on the preconditioner, only iteration counts.
 #include <algorithm>
+#include <stdlib.h>
+
+#include <cooperative_groups.h>
 
 #include "fedmx_internal.h"
+
+namespace cg = cooperative_groups;
 
 int fedmx_halo_exchange_internal(fedmx_ctx *ctx, double *d_vec, int n_comp);
 int fedmx_global_sum(fedmx_ctx *ctx, double *d_buf, int n);
 
 namespace {
 
-enum { MODE_MULT = 0, MODE_RESID = 1, MODE_JACOBI = 2, MODE_ADD = 3 };
+enum { MODE_MULT = 0, MODE_RESID = 1, MODE_JACOBI = 2, MODE_ADD = 3, MODE_JACOBI_OUT = 4 };
 
+// MODE_JACOBI_OUT: the last sweep of the cycle writes its result straight into component `yo` of the node-interleaved
+// preconditioned vector (y[row*ys + yo]) instead of the level's iterate.
 template <int MODE>
 __global__ void __launch_bounds__(128) ssell_kernel(ScalarSell A, const double *__restrict__ x, const double *__restrict__ b,
-                                                    const double *__restrict__ dinv, double omega, double *__restrict__ y) {
+                                                    const double *__restrict__ dinv, double omega, double *__restrict__ y,
+                                                    int ys = 1, int yo = 0) {
     const int64_t row = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     const int64_t s = row / FEDMX_SLICE;
     const int lane = int(row % FEDMX_SLICE);
@@ -37,7 +45,30 @@ __global__ void __launch_bounds__(128) ssell_kernel(ScalarSell A, const double *
     if (MODE == MODE_MULT) y[row] = t;
     else if (MODE == MODE_RESID) y[row] = b[row] - t;
     else if (MODE == MODE_JACOBI) y[row] = x[row] + omega * dinv[row] * (b[row] - t);
+    else if (MODE == MODE_JACOBI_OUT) y[row * ys + yo] = x[row] + omega * dinv[row] * (b[row] - t);
     else y[row] += t;
+}
+
+// y = M x with LPR lanes per row (restriction rows are 40-60 entries long: one thread per row is latency-bound)
+template <int LPR>
+__global__ void __launch_bounds__(128) ssell_mult_split_kernel(ScalarSell A, const double *__restrict__ x, double *__restrict__ y) {
+    const int64_t w = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t row = w / LPR;
+    const int part = int(w % LPR);
+    double t = 0.0;
+    if (row < A.n_rows) {
+        const int64_t s = row / FEDMX_SLICE;
+        const int lane = int(row % FEDMX_SLICE);
+        const int width = A.slice_width[s];
+        const int64_t base = A.slice_ptr[s] + lane;
+        for (int k = part; k < width; k += LPR) {
+            const int64_t e = base + int64_t(k) * FEDMX_SLICE;
+            t = fma(double(A.val[e]), __ldg(x + A.col[e]), t);
+        }
+    }
+#pragma unroll
+    for (int o = LPR >> 1; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (part == 0 && row < A.n_rows) y[row] = t;
 }
 
 __global__ void first_sweep_kernel(const double *__restrict__ b, const double *__restrict__ dinv, double omega,
@@ -90,36 +121,69 @@ struct CoarseLevelDev {
     double *b, *x, *x2, *r;
 };
 
-__device__ __forceinline__ double ssell_row(const ScalarSell &M, int64_t row, const double *x) {
+// Partial row product of a scalar SELL-32 matrix: lane `part` of the LPR lanes that share the row takes the stored
+// entries k = part, part+LPR, ...; the caller sums the parts with shuffles.  Coarse levels are latency-bound (one thread
+// walking a 40-60 entry restriction row costs ~15 us regardless of the level size), so rows are split across lanes there.
+__device__ __forceinline__ double ssell_row_part(const ScalarSell &M, int64_t row, int part, int lpr, const double *x) {
     const int64_t s = row / FEDMX_SLICE;
     const int lane = int(row % FEDMX_SLICE);
     const int width = M.slice_width[s];
     const int64_t base = M.slice_ptr[s] + lane;
     double t = 0.0;
-    for (int k = 0; k < width; ++k) {
+    for (int k = part; k < width; k += lpr) {
         const int64_t e = base + int64_t(k) * FEDMX_SLICE;
         t = fma(double(M.val[e]), x[M.col[e]], t);
     }
     return t;
 }
 
+__device__ __forceinline__ double group_sum(double t, int lpr) {
+    for (int o = lpr >> 1; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    return t;
+}
+
+__device__ __forceinline__ int pick_lpr(int64_t n, int nt, int cap) {
+    int l = 1;
+    while (l < cap && int64_t(2 * l) * n <= nt) l <<= 1;
+    return l;
+}
+
+// One thread-block CLUSTER walks levels [first, last] of the V-cycle; the phases are separated by hardware cluster
+// barriers (barrier.cluster arrive.release / wait.acquire, ~0.3 us) instead of kernel boundaries (~3-5 us each, and
+// 5 launches per level).  tid/nt run over the whole cluster.  `op(row, sum)` consumes the finished row product.
+template <class Op>
+__device__ __forceinline__ void for_rows(const ScalarSell &M, int64_t n, const double *x, int tid, int nt, int lpr_cap, Op op) {
+    const int lpr = pick_lpr(n, nt, lpr_cap);
+    const int64_t items = ((n * lpr + 31) / 32) * 32;            // whole warps iterate together (shuffles)
+    for (int64_t w = tid; w < items; w += nt) {
+        const int64_t row = w / lpr;
+        const int part = int(w % lpr);
+        double t = row < n ? ssell_row_part(M, row, part, lpr, x) : 0.0;
+        t = group_sum(t, lpr);
+        if (part == 0 && row < n) op(row, t);
+    }
+}
+
 __global__ void __launch_bounds__(1024) coarse_vcycle_kernel(const CoarseLevelDev *L, int nl, int nu, const double *__restrict__ cinv) {
-    const int tid = threadIdx.x, nt = blockDim.x;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int nt = int(cluster.num_blocks()) * blockDim.x;
+    const int tid = int(cluster.block_rank()) * blockDim.x + threadIdx.x;
     // down: pre-smooth (zero initial guess), residual, restriction.  The current iterate always ends up in lv.x.
     for (int l = 0; l < nl - 1; ++l) {
         const CoarseLevelDev &lv = L[l];
         for (int64_t i = tid; i < lv.n; i += nt) lv.x[i] = lv.omega * lv.dinv[i] * lv.b[i];
-        __syncthreads();
+        cluster.sync();
         for (int sweep = 1; sweep < nu; ++sweep) {
-            for (int64_t i = tid; i < lv.n; i += nt) lv.x2[i] = lv.x[i] + lv.omega * lv.dinv[i] * (lv.b[i] - ssell_row(lv.A, i, lv.x));
-            __syncthreads();
+            for_rows(lv.A, lv.n, lv.x, tid, nt, 8, [&](int64_t i, double t) { lv.x2[i] = lv.x[i] + lv.omega * lv.dinv[i] * (lv.b[i] - t); });
+            cluster.sync();
             for (int64_t i = tid; i < lv.n; i += nt) lv.x[i] = lv.x2[i];
-            __syncthreads();
+            cluster.sync();
         }
-        for (int64_t i = tid; i < lv.n; i += nt) lv.r[i] = lv.b[i] - ssell_row(lv.A, i, lv.x);
-        __syncthreads();
-        for (int64_t i = tid; i < lv.n_coarse; i += nt) L[l + 1].b[i] = ssell_row(lv.R, i, lv.r);
-        __syncthreads();
+        for_rows(lv.A, lv.n, lv.x, tid, nt, 8, [&](int64_t i, double t) { lv.r[i] = lv.b[i] - t; });
+        cluster.sync();
+        double *bc = L[l + 1].b;
+        for_rows(lv.R, lv.n_coarse, lv.r, tid, nt, 32, [&](int64_t i, double t) { bc[i] = t; });
+        cluster.sync();
     }
     {   // coarsest level: dense inverse, one warp per row
         const CoarseLevelDev &lc = L[nl - 1];
@@ -132,18 +196,19 @@ __global__ void __launch_bounds__(1024) coarse_vcycle_kernel(const CoarseLevelDe
             for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
             if (lane == 0) lc.x[row] = acc;
         }
-        __syncthreads();
+        cluster.sync();
     }
     // up: prolongation + correction, post-smooth
     for (int l = nl - 2; l >= 0; --l) {
         const CoarseLevelDev &lv = L[l];
-        for (int64_t i = tid; i < lv.n; i += nt) lv.x[i] += ssell_row(lv.P, i, L[l + 1].x);
-        __syncthreads();
+        const double *xc = L[l + 1].x;
+        for_rows(lv.P, lv.n, xc, tid, nt, 4, [&](int64_t i, double t) { lv.x[i] += t; });
+        cluster.sync();
         for (int sweep = 0; sweep < nu; ++sweep) {
-            for (int64_t i = tid; i < lv.n; i += nt) lv.x2[i] = lv.x[i] + lv.omega * lv.dinv[i] * (lv.b[i] - ssell_row(lv.A, i, lv.x));
-            __syncthreads();
+            for_rows(lv.A, lv.n, lv.x, tid, nt, 8, [&](int64_t i, double t) { lv.x2[i] = lv.x[i] + lv.omega * lv.dinv[i] * (lv.b[i] - t); });
+            cluster.sync();
             for (int64_t i = tid; i < lv.n; i += nt) lv.x[i] = lv.x2[i];
-            __syncthreads();
+            cluster.sync();
         }
     }
 }
@@ -188,17 +253,19 @@ int upload_ssell(fedmx_ctx *ctx, ScalarSell &M, int64_t n_rows, int64_t n_cols, 
 }
 
 template <int MODE>
-void launch_ssell(fedmx_ctx *ctx, const ScalarSell &A, const double *x, const double *b, const double *dinv, double omega, double *y) {
+void launch_ssell(fedmx_ctx *ctx, const ScalarSell &A, const double *x, const double *b, const double *dinv, double omega, double *y,
+                  int ys = 1, int yo = 0) {
     const int threads = 128;
     const unsigned blocks = unsigned((A.n_slices * FEDMX_SLICE + threads - 1) / threads);
-    ssell_kernel<MODE><<<blocks, threads, 0, ctx->stream>>>(A, x, b, dinv, omega, y);
+    ssell_kernel<MODE><<<blocks, threads, 0, ctx->stream>>>(A, x, b, dinv, omega, y, ys, yo);
     ctx->launches++;
 }
 
 }  // namespace
 
 // Levels with at most kFuseRows rows are walked by the single-CTA kernel (they are launch-latency bound otherwise).
-constexpr int64_t kFuseRows = 3000;   // larger levels are faster as separate launches (one CTA is latency-bound on the gathers)
+static const int64_t kFuseRows = getenv("FEDMX_FUSE_ROWS") ? atoll(getenv("FEDMX_FUSE_ROWS")) : 3000;  // one cluster of 8 CTAs; measured on B200: 3000, 8000 and 80000 rows give 26.8 / 26.9 / 29.9 ms per step (8 SMs cannot feed larger levels)
+constexpr int kClusterSize = 8;
 
 static int setup_coarse_fusion(fedmx_ctx *ctx) {
     auto &L = ctx->amg_levels;
@@ -224,8 +291,10 @@ static int setup_coarse_fusion(fedmx_ctx *ctx) {
     return FEDMX_OK;
 }
 
-// One V-cycle with zero initial guess: x_0 = Vcycle(b_0); b_0 = levels[0].b, result in levels[0].x
-int fedmx_amg_vcycle(fedmx_ctx *ctx) {
+// One V-cycle with zero initial guess: x_0 = Vcycle(b_0); b_0 = levels[0].b.  The result goes to component z_off of the
+// node-interleaved vector z_out (stride z_stride): written by the last smoothing sweep itself when the finest level runs
+// as separate launches, by a small scatter kernel otherwise.
+int fedmx_amg_vcycle(fedmx_ctx *ctx, double *z_out, int z_stride, int z_off) {
     auto &L = ctx->amg_levels;
     const int nl = int(L.size());
     FEDMX_REQUIRE(ctx, nl > 0 && ctx->amg_coarse_inv, "AMG hierarchy not set");
@@ -246,20 +315,48 @@ int fedmx_amg_vcycle(fedmx_ctx *ctx) {
         const bool dist = (l == 0 && ctx->n_ranks > 1);
         if (dist && (rc = fedmx_halo_exchange_internal(ctx, lv.x, 1))) return rc;      // ghosts of x for A x
         launch_ssell<MODE_RESID>(ctx, lv.A, lv.x, lv.b, nullptr, 0.0, lv.r);
-        launch_ssell<MODE_MULT>(ctx, lv.R, lv.r, nullptr, nullptr, 0.0, L[l + 1].b);
+        {
+            constexpr int LPR = 4;
+            const unsigned rb = unsigned((lv.R.n_rows * LPR + 127) / 128);
+            ssell_mult_split_kernel<LPR><<<rb, 128, 0, ctx->stream>>>(lv.R, lv.r, L[l + 1].b);
+            ctx->launches++;
+        }
         // distributed fine level: R holds only this rank's fine columns; the coarse right-hand side is the sum over ranks
         if (dist && (rc = fedmx_global_sum(ctx, L[l + 1].b, int(L[l + 1].n)))) return rc;
     }
-    coarse_vcycle_kernel<<<1, 1024, 0, ctx->stream>>>((const CoarseLevelDev *)ctx->d_coarse_levels, ctx->coarse_count, nu, ctx->amg_coarse_inv);
-    ctx->launches++;
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(kClusterSize);
+        cfg.blockDim = dim3(1024);
+        cfg.stream = ctx->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = kClusterSize;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        FEDMX_CHECK_CUDA(ctx, cudaLaunchKernelEx(&cfg, coarse_vcycle_kernel, (const CoarseLevelDev *)ctx->d_coarse_levels,
+                                                 ctx->coarse_count, nu, (const double *)ctx->amg_coarse_inv));
+        ctx->launches++;
+    }
     for (int l = cf - 1; l >= 0; --l) {
         AmgLevel &lv = L[l];
         launch_ssell<MODE_ADD>(ctx, lv.P, L[l + 1].x, nullptr, nullptr, 0.0, lv.x);
         for (int sweep = 0; sweep < nu; ++sweep) {
             if (l == 0 && ctx->n_ranks > 1 && (rc = fedmx_halo_exchange_internal(ctx, lv.x, 1))) return rc;
+            if (l == 0 && sweep == nu - 1) {
+                launch_ssell<MODE_JACOBI_OUT>(ctx, lv.A, lv.x, lv.b, lv.dinv, lv.omega, z_out, z_stride, z_off);
+                break;
+            }
             launch_ssell<MODE_JACOBI>(ctx, lv.A, lv.x, lv.b, lv.dinv, lv.omega, lv.x2);
             std::swap(lv.x, lv.x2);
         }
+    }
+    if (cf == 0) {                                          // the whole hierarchy ran inside the fused kernel
+        const int64_t n = L[0].n;
+        comp_scatter_kernel<<<unsigned((n + 255) / 256), 256, 0, ctx->stream>>>(L[0].x, z_out, z_stride, z_off, n);
+        ctx->launches++;
     }
     FEDMX_CHECK_CUDA(ctx, cudaGetLastError());
     return FEDMX_OK;
@@ -290,11 +387,23 @@ int fedmx_precond_apply(fedmx_ctx *ctx, const double *d_r, double *d_z) {
         }
         ctx->launches++;
     }
-    if ((rc = fedmx_amg_vcycle(ctx))) return rc;
-    comp_scatter_kernel<<<unsigned((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->amg_levels[0].x, d_z, ctx->n_eq, comp, n);
-    ctx->launches++;
-    FEDMX_CHECK_CUDA(ctx, cudaGetLastError());
-    return FEDMX_OK;
+    return fedmx_amg_vcycle(ctx, d_z, ctx->n_eq, comp);
+}
+
+// Krylov fast path of the two-stage preconditioner: z = M^-1 A v with the node-block Jacobi stage and the extraction of the
+// multigrid right-hand side fused into the SpMV epilogue, and the multigrid result written by its last smoothing sweep.
+int fedmx_two_stage_after_spmv(fedmx_ctx *ctx, const double *d_v, double *d_z) {
+    int rc;
+    if ((rc = fedmx_spmv_precond(ctx, d_v, d_z, true, ctx->amg_levels[0].b, ctx->amg_comp))) return rc;
+    ProfScope prof(ctx, FEDMX_PROF_PRECOND);
+    return fedmx_amg_vcycle(ctx, d_z, ctx->n_eq, ctx->amg_comp);
+}
+
+extern "C" int fedmx_pc_apply(fedmx_ctx *ctx, const double *d_r, double *d_z) {
+    if (!ctx) return FEDMX_EINVAL;
+    FEDMX_REQUIRE(ctx, d_r && d_z && d_r != d_z, "fedmx_pc_apply: null or aliased vectors");
+    FEDMX_REQUIRE(ctx, ctx->d_dinv, "fedmx_pc_apply: no matrix assembled");
+    return fedmx_precond_apply(ctx, d_r, d_z);
 }
 
 extern "C" int fedmx_amg_reset(fedmx_ctx *ctx) {

@@ -24,6 +24,7 @@ extern "C" int fedmx_ctx_destroy(fedmx_ctx *ctx) {
     if (!ctx) return FEDMX_EINVAL;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    fedmx_peer_destroy(ctx);
     for (void *p : ctx->owned_device) cudaFree(p);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     for (auto &pool : ctx->prof_ev)

@@ -12,6 +12,8 @@
 #define FEDMX_MAX_BC 16
 #define FEDMX_SLICE 32
 #define FEDMX_MAX_REFS 48
+#define FEDMX_MAX_RANKS 8
+#define FEDMX_PEER_AR_MAX 128
 
 // Indirect coefficient reference of a plug-in model: component `offset` of a node-interleaved vector with `stride` comps
 struct FieldRef {
@@ -86,6 +88,20 @@ struct HaloPlan {
     int64_t n_send = 0, n_recv = 0;
 };
 
+// Symmetric peer heap (CUDA IPC) for the NVLink collectives of fedmx_peer.cu
+struct PeerState {
+    bool on = false, opened = false, halo_ready = false;
+    char *base = nullptr;
+    size_t bytes = 0;
+    char *bases[FEDMX_MAX_RANKS] = {};
+    size_t off_flags = 0, off_ar_slots = 0, off_halo = 0, off_big_in = 0, off_big_out = 0;
+    int64_t halo_cap = 0, big_cap = 0;
+    unsigned long long halo_epoch = 0, ar_epoch = 0, big_epoch = 0;
+    std::vector<int32_t> remote_off;
+    unsigned int *d_counter = nullptr;
+    int *h_err = nullptr, *d_err = nullptr;
+};
+
 struct fedmx_ctx {
     int device = 0;
     cudaStream_t stream = 0;
@@ -141,6 +157,7 @@ struct fedmx_ctx {
     void *nccl_comm = nullptr;
     int n_ranks = 1, rank = 0;
     HaloPlan halo;
+    PeerState peer;
 };
 
 #define FEDMX_CHECK_CUDA(ctx, expr)                                                          \
@@ -194,6 +211,10 @@ int fedmx_profile_flush(fedmx_ctx *ctx, int kind);
 // internal entry points shared between translation units
 int fedmx_ensure_workspace(fedmx_ctx *ctx, int restart);
 int fedmx_update_block_jacobi(fedmx_ctx *ctx);
-int fedmx_spmv_precond(fedmx_ctx *ctx, const double *d_x, double *d_y, bool precond);
+int fedmx_spmv_precond(fedmx_ctx *ctx, const double *d_x, double *d_y, bool precond, double *d_rhs_c = nullptr, int comp = 0);
+int fedmx_two_stage_after_spmv(fedmx_ctx *ctx, const double *d_v, double *d_z);
 int fedmx_norm2_local(fedmx_ctx *ctx, const double *d_x, int64_t n, double *out, bool global);
 int fedmx_precond_apply(fedmx_ctx *ctx, const double *d_r, double *d_z);
+int fedmx_peer_halo_exchange(fedmx_ctx *ctx, double *d_vec, int n_comp);
+int fedmx_peer_allreduce(fedmx_ctx *ctx, double *d_buf, int64_t n);
+int fedmx_peer_destroy(fedmx_ctx *ctx);

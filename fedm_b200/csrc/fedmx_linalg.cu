@@ -38,10 +38,12 @@ __device__ __forceinline__ double block_sum(double v, double *smem) {
 }
 
 // ---- SpMV: y = A x  or  y = Dinv (A x), one thread per block row, SELL-32 entry-major storage ----------
-template <int NEQ, bool PRECOND>
+// EXTRACT: additionally rhs_c[row] = (A x)[NEQ*row + comp], the raw right-hand side of the multigrid stage of the
+// two-stage preconditioner (saves a separate pass over the residual and the block inverses).
+template <int NEQ, bool PRECOND, bool EXTRACT>
 __global__ void __launch_bounds__(128) spmv_kernel(SellView S, const double *__restrict__ val,
                                                    const double *__restrict__ dinv, const double *__restrict__ x,
-                                                   double *__restrict__ y) {
+                                                   double *__restrict__ y, int comp, double *__restrict__ rhs_c) {
     constexpr int NB = NEQ * NEQ;
     const int64_t row = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     const int64_t s = row / FEDMX_SLICE;
@@ -65,6 +67,11 @@ __global__ void __launch_bounds__(128) spmv_kernel(SellView S, const double *__r
             for (int l = 0; l < NEQ; ++l) acc[i] = fma(__ldcs(v + (i * NEQ + l) * FEDMX_SLICE), xc[l], acc[i]);
     }
     if (row >= S.n_rows) return;
+    if (EXTRACT) {
+#pragma unroll
+        for (int i = 0; i < NEQ; ++i)
+            if (i == comp) rhs_c[row] = acc[i];
+    }
     if (PRECOND) {
         const double *d = dinv + s * FEDMX_SLICE * NB + lane;
         double z[NEQ];
@@ -401,14 +408,16 @@ int fedmx_update_block_jacobi(fedmx_ctx *ctx) {
     return FEDMX_OK;
 }
 
-int fedmx_spmv_precond(fedmx_ctx *ctx, const double *d_x, double *d_y, bool precond) {
+int fedmx_spmv_precond(fedmx_ctx *ctx, const double *d_x, double *d_y, bool precond, double *d_rhs_c, int comp) {
     const int threads = 128;
     const unsigned blocks = unsigned((ctx->sell.n_slices * FEDMX_SLICE + threads - 1) / threads);
     ProfScope prof(ctx, FEDMX_PROF_SPMV);
+    FEDMX_REQUIRE(ctx, !d_rhs_c || precond, "spmv: component extraction is only built for the preconditioned variant");
 #define SPMV_CASE(N)                                                                                              \
     case N:                                                                                                       \
-        if (precond) spmv_kernel<N, true><<<blocks, threads, 0, ctx->stream>>>(ctx->sell, ctx->d_val, ctx->d_dinv, d_x, d_y); \
-        else spmv_kernel<N, false><<<blocks, threads, 0, ctx->stream>>>(ctx->sell, ctx->d_val, ctx->d_dinv, d_x, d_y);        \
+        if (d_rhs_c) spmv_kernel<N, true, true><<<blocks, threads, 0, ctx->stream>>>(ctx->sell, ctx->d_val, ctx->d_dinv, d_x, d_y, comp, d_rhs_c); \
+        else if (precond) spmv_kernel<N, true, false><<<blocks, threads, 0, ctx->stream>>>(ctx->sell, ctx->d_val, ctx->d_dinv, d_x, d_y, 0, nullptr); \
+        else spmv_kernel<N, false, false><<<blocks, threads, 0, ctx->stream>>>(ctx->sell, ctx->d_val, ctx->d_dinv, d_x, d_y, 0, nullptr);        \
         break;
     switch (ctx->n_eq) {
         SPMV_CASE(1)
@@ -531,6 +540,7 @@ int fedmx_norm2_local(fedmx_ctx *ctx, const double *d_x, int64_t n, double *out,
     if (global && ctx->n_ranks > 1 && (rc = fedmx_global_sum(ctx, ctx->d_hess + 2048, 1))) return rc;
     FEDMX_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + 2048, ctx->d_hess + 2048, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     FEDMX_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    FEDMX_REQUIRE(ctx, !(ctx->peer.h_err && *ctx->peer.h_err), "peer-memory collective timed out waiting for a neighbour's flag");
     *out = sqrt(ctx->h_pinned[2048]);
     return FEDMX_OK;
 }

@@ -64,8 +64,7 @@ int gmres_impl(fedmx_ctx *ctx, const double *d_b, double *d_x, int restart, doub
             if (ctx->precond_kind == 0) {
                 if ((rc = fedmx_spmv_precond(ctx, Vk, w, true))) return rc;       // block Jacobi fused into the SpMV epilogue
             } else {
-                if ((rc = fedmx_spmv_precond(ctx, Vk, ctx->d_tmp, false))) return rc;
-                if ((rc = fedmx_precond_apply(ctx, ctx->d_tmp, w))) return rc;
+                if ((rc = fedmx_two_stage_after_spmv(ctx, Vk, w))) return rc;
             }
             {
                 ProfScope prof(ctx, FEDMX_PROF_ORTHO);
@@ -76,6 +75,7 @@ int gmres_impl(fedmx_ctx *ctx, const double *d_b, double *d_x, int restart, doub
             }
             FEDMX_CHECK_CUDA(ctx, cudaMemcpyAsync(hp, dh, 65 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
             FEDMX_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            FEDMX_REQUIRE(ctx, !(ctx->peer.h_err && *ctx->peer.h_err), "peer-memory collective timed out waiting for a neighbour's flag");
             const double hk1 = sqrt(hp[64]);
             for (int i = 0; i <= k; ++i) Hm(i, k) = hp[i];
             Hm(k + 1, k) = hk1;

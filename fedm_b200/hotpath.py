@@ -117,8 +117,10 @@ class HotPath:
         Partitioned runs (local_mesh given): the owned rows of all ranks are gathered into the global block, every
         rank builds the identical global hierarchy, keeps its own slice of the finest level (halo exchange per
         smoothing step) and a replica of all coarser levels (the restricted residual is all-reduced)."""
+        import os
         import scipy.sparse as sp
         from . import amg
+        nu = int(os.environ.get("FEDMX_AMG_NU", nu))
         Kloc = self.matrix_component(comp, comp)
         bc = np.asarray(bc_nodes, dtype=np.int64)
         i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
@@ -184,7 +186,14 @@ class HotPath:
         self._ck(self.lib.fedmx_amg_set_coarse(self.h, ci.shape[0], _np_ptr(ci)))
         self._ck(self.lib.fedmx_precond_set(self.h, 1, comp, nu))
         self.amg_levels = [lv["A"].shape[0] for lv in levels]
+        self.amg_host = (levels, coarse_inv)             # kept for tests (numpy reference cycle)
         return self.amg_levels
+
+    def pc_apply(self, r, z=None):
+        """z = M^-1 r with the current preconditioner (PCApply)."""
+        z = self.new_vector() if z is None else z
+        self._ck(self.lib.fedmx_pc_apply(self.h, _ptr(r), _ptr(z)))
+        return z
 
     def use_block_jacobi(self):
         self._ck(self.lib.fedmx_precond_set(self.h, 0, 0, 1))
@@ -293,6 +302,34 @@ class HotPath:
 
     def halo_exchange(self, vec, n_comp=None):
         self._ck(self.lib.fedmx_halo_exchange(self.h, _ptr(vec), self.n_eq if n_comp is None else n_comp))
+
+    def allreduce_sum(self, buf, n=None):
+        self._ck(self.lib.fedmx_allreduce_sum(self.h, _ptr(buf), buf.numel() if n is None else n))
+
+    def peer_init(self, world, rank, neighbor_ranks, recv_ptr, n_global_vertices):
+        """NVLink peer-memory transport (fedmx_peer.cu): allocate the symmetric heap, exchange the CUDA IPC handles and the
+        per-neighbour staging offsets over torch.distributed, map every peer.  Call after comm_init + set_halo."""
+        import torch.distributed as dist
+        nb = [int(q) for q in neighbor_ranks]
+        rp = [int(v) for v in recv_ptr]
+        plans = [None] * world
+        dist.all_gather_object(plans, (nb, rp))
+        halo_cap = 5 * max(p[1][-1] for p in plans) + 64          # FEDMX_MAX_EQ components per ghost node
+        big_cap = int(n_global_vertices) // 2 + 1024              # restricted multigrid residual (level 1 of the hierarchy)
+        handle = C.create_string_buffer(64)
+        self._ck(self.lib.fedmx_peer_create(self.h, halo_cap, big_cap, handle))
+        handles = [None] * world
+        dist.all_gather_object(handles, handle.raw)
+        self._ck(self.lib.fedmx_peer_open(self.h, b"".join(handles)))
+        remote = np.array([plans[q][1][plans[q][0].index(rank)] for q in nb], dtype=np.int32)
+        self._ck(self.lib.fedmx_peer_halo_set(self.h, len(nb), _np_ptr(remote)))
+        dist.barrier()
+
+    def peer_enable(self, on=True):
+        self._ck(self.lib.fedmx_peer_enable(self.h, 1 if on else 0))
+
+    def peer_error(self):
+        return int(self.lib.fedmx_peer_error(self.h))
 
 
 def pi34_step(dt, err, tol, dt_min, dt_max):

@@ -97,6 +97,9 @@ class StreamerCase:
         hot.comm_init(self.world, self.rank, ident)
         lm = self.local
         hot.set_halo(lm.neighbors, lm.send_ptr, lm.send_nodes, lm.recv_ptr, lm.recv_nodes)
+        import os
+        if os.environ.get("FEDMX_PEER", "1") != "0":       # NVLink peer-memory collectives (default); 0 = NCCL only
+            hot.peer_init(self.world, self.rank, lm.neighbors, lm.recv_ptr, lm.n_global_vertices)
 
     # ---- initial condition + initial Poisson solve ---------------------------------------------------
     def initial_log_densities(self):

@@ -137,6 +137,8 @@ int fedmx_gmres(fedmx_ctx *ctx, const double *d_b, double *d_x, int restart, dou
  * inverse goes to fedmx_amg_set_coarse).  fedmx_matrix_get_component copies entry (i,j) of every stored block
  * (block-CSR order) so that the host can extract that block from an assembled Jacobian. */
 int fedmx_precond_set(fedmx_ctx *ctx, int kind, int comp, int nu);
+/* z = M^-1 r with the current preconditioner (PETSc PCApply); r and z are distinct device vectors of the state layout. */
+int fedmx_pc_apply(fedmx_ctx *ctx, const double *d_r, double *d_z);
 int fedmx_amg_reset(fedmx_ctx *ctx);
 int fedmx_amg_add_level(fedmx_ctx *ctx, int64_t n, const double *h_dinv, double omega,
                         const int32_t *a_rowptr, const int32_t *a_col, const double *a_val, int64_t n_coarse,
@@ -215,6 +217,21 @@ int fedmx_halo_set(fedmx_ctx *ctx, int n_neighbors, const int32_t *h_neighbor_ra
  * fedm/functions.py:625; VecGhostUpdate inside MatMult). */
 int fedmx_halo_exchange(fedmx_ctx *ctx, double *d_vec, int n_comp);
 int fedmx_allreduce_sum(fedmx_ctx *ctx, double *d_buf, int n);
+
+/* NVLink peer-memory transport for the collectives above (CUDA IPC symmetric heap, one per context): once opened,
+ * fedmx_halo_exchange / fedmx_allreduce_sum and the solver's internal collectives store straight into the
+ * neighbours' memory and synchronise with release/acquire flags instead of going through NCCL (latency: an NVLink
+ * round trip instead of a collective launch).  Replaces the same MPI calls as above.
+ *   create: allocates the heap (halo_capacity, big_capacity in doubles, identical on all ranks) -> 64-byte IPC handle
+ *   open:   handles of all ranks, rank-major [n_ranks][64] (gathered by the host's own plumbing)
+ *   halo_set: per neighbour (order of fedmx_halo_set) the node offset of this rank's segment in the NEIGHBOUR's
+ *             receive list (= the neighbour's recv_ptr entry for this rank)
+ *   enable: switch the peer transport on/off (off = NCCL);  error: 1 after a flag wait timed out */
+int fedmx_peer_create(fedmx_ctx *ctx, int64_t halo_capacity, int64_t big_capacity, char handle_out[64]);
+int fedmx_peer_open(fedmx_ctx *ctx, const char *handles);
+int fedmx_peer_halo_set(fedmx_ctx *ctx, int n_neighbors, const int32_t *h_remote_offsets);
+int fedmx_peer_enable(fedmx_ctx *ctx, int on);
+int fedmx_peer_error(fedmx_ctx *ctx);
 
 /* ---- instrumentation ------------------------------------------------------------------------------- */
 /* Number of kernels this library launched since the last call with reset != 0. */
