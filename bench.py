@@ -117,6 +117,7 @@ def main():
     ap.add_argument("--n", type=int, default=FULL_N, help="grid size (n x n cells pairs); 1825 -> 10.0M DOF")
     ap.add_argument("--sample-n", type=int, default=0, help="CPU-baseline sample grid (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-detail", action="store_true", help="nested event timing of multigrid levels and collectives")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -154,7 +155,7 @@ def main():
     for _ in range(args.warmup):
         case.step()
     # ---- timed region: K accepted steps, device-timed, max over ranks
-    hot.profile_enable(True)
+    hot.profile_enable(2 if args.profile_detail else 1)
     hot.profile_get()
     hot.launch_count(reset=True)
     n_stats0 = len(case.stats)
@@ -225,7 +226,10 @@ def main():
         "jacobian_assembly_gdof_s": (dof * n_aj / (ms_aj * 1e-3) / 1e9) if ms_aj > 0 else None,
         "residual_assembly_gdof_s": (dof * n_ar / (ms_ar * 1e-3) / 1e9) if ms_ar > 0 else None,
         "kernel_ms_per_step": {"spmv": ms_sp / args.steps, "orthogonalisation": ms_or / args.steps,
-                               "preconditioner": ms_pc / args.steps, "assemble_jacobian": ms_aj / args.steps, "assemble_residual": ms_ar / args.steps},
+                               "preconditioner": ms_pc / args.steps, "assemble_jacobian": ms_aj / args.steps, "assemble_residual": ms_ar / args.steps,
+                               # nested break-down: multigrid levels inside "preconditioner", collectives inside all classes
+                               "mg_fine": prof["mg_fine"][1] / args.steps, "mg_mid": prof["mg_mid"][1] / args.steps,
+                               "mg_coarse": prof["mg_coarse"][1] / args.steps, "comm": prof["comm"][1] / args.steps},
         "roofline": {"kernel": "spmv_kernel<3,true> (SELL-32 block SpMV + block-Jacobi)", "bound": "hbm",
                      "achieved": spmv_gbs, "peak": peak, "unit": "GB/s", "frac": spmv_gbs / peak if spmv_gbs else None,
                      "traffic": None, "peak_source": peak_src, "launches": n_sp,

@@ -303,6 +303,7 @@ int fedmx_amg_vcycle(fedmx_ctx *ctx, double *z_out, int z_stride, int z_off) {
     if (ctx->coarse_first < 0 && (rc = setup_coarse_fusion(ctx))) return rc;
     const int cf = ctx->coarse_first;
     for (int l = 0; l < cf; ++l) {
+        ProfScope lprof(ctx, l == 0 ? FEDMX_PROF_MG_FINE : FEDMX_PROF_MG_MID);
         AmgLevel &lv = L[l];
         const unsigned vb = unsigned((lv.n + 255) / 256);
         first_sweep_kernel<<<vb, 256, 0, ctx->stream>>>(lv.b, lv.dinv, lv.omega, lv.x, lv.n);
@@ -325,6 +326,7 @@ int fedmx_amg_vcycle(fedmx_ctx *ctx, double *z_out, int z_stride, int z_off) {
         if (dist && (rc = fedmx_global_sum(ctx, L[l + 1].b, int(L[l + 1].n)))) return rc;
     }
     {
+        ProfScope cprof(ctx, FEDMX_PROF_MG_COARSE);
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(kClusterSize);
         cfg.blockDim = dim3(1024);
@@ -341,6 +343,7 @@ int fedmx_amg_vcycle(fedmx_ctx *ctx, double *z_out, int z_stride, int z_off) {
         ctx->launches++;
     }
     for (int l = cf - 1; l >= 0; --l) {
+        ProfScope lprof(ctx, l == 0 ? FEDMX_PROF_MG_FINE : FEDMX_PROF_MG_MID);
         AmgLevel &lv = L[l];
         launch_ssell<MODE_ADD>(ctx, lv.P, L[l + 1].x, nullptr, nullptr, 0.0, lv.x);
         for (int sweep = 0; sweep < nu; ++sweep) {

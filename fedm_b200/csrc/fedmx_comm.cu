@@ -91,6 +91,7 @@ extern "C" int fedmx_halo_set(fedmx_ctx *ctx, int n_neighbors, const int32_t *h_
 int fedmx_halo_exchange_internal(fedmx_ctx *ctx, double *d_vec, int n_comp) {
     HaloPlan &H = ctx->halo;
     if (ctx->n_ranks <= 1 || H.n_neighbors == 0) return FEDMX_OK;
+    ProfScope prof(ctx, FEDMX_PROF_COMM);
     if (ctx->peer.on && ctx->peer.halo_ready) return fedmx_peer_halo_exchange(ctx, d_vec, n_comp);   // NVLink peer stores
     FEDMX_REQUIRE(ctx, ctx->nccl_comm, "halo exchange: communicator not initialised");
     FEDMX_REQUIRE(ctx, n_comp >= 1 && n_comp <= FEDMX_MAX_EQ, "halo exchange: bad component count");
@@ -120,6 +121,7 @@ int fedmx_halo_exchange_internal(fedmx_ctx *ctx, double *d_vec, int n_comp) {
 
 int fedmx_global_sum(fedmx_ctx *ctx, double *d_buf, int n) {
     if (ctx->n_ranks <= 1) return FEDMX_OK;
+    ProfScope prof(ctx, FEDMX_PROF_COMM);
     if (ctx->peer.on && (n <= FEDMX_PEER_AR_MAX || n <= ctx->peer.big_cap)) return fedmx_peer_allreduce(ctx, d_buf, n);
     FEDMX_REQUIRE(ctx, ctx->nccl_comm, "allreduce: communicator not initialised");
     FEDMX_CHECK_NCCL(ctx, ncclAllReduce(d_buf, d_buf, size_t(n), ncclDouble, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->stream));

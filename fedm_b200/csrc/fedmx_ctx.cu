@@ -50,7 +50,7 @@ extern "C" int64_t fedmx_launch_count(fedmx_ctx *ctx, int reset) {
 
 // ---- profiling -----------------------------------------------------------------------------------------
 ProfScope::ProfScope(fedmx_ctx *ctx, int k) : c(ctx), kind(k) {
-    if (!c->prof_on) return;
+    if (!c->prof_on || (k >= FEDMX_PROF_MG_FINE && c->prof_on < 2)) return;
     auto &pool = c->prof_ev[kind];
     if (c->prof_used[kind] + 2 > pool.size()) {
         if (pool.size() >= 8192) fedmx_profile_flush(c, kind);
@@ -76,7 +76,7 @@ int fedmx_profile_flush(fedmx_ctx *ctx, int kind) {
 }
 extern "C" int fedmx_profile_enable(fedmx_ctx *ctx, int on) {
     if (!ctx) return FEDMX_EINVAL;
-    ctx->prof_on = on != 0;
+    ctx->prof_on = on;
     return FEDMX_OK;
 }
 extern "C" int fedmx_profile_get(fedmx_ctx *ctx, int kind, int64_t *count, double *total_ms) {

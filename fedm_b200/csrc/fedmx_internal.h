@@ -148,11 +148,11 @@ struct fedmx_ctx {
     void *d_coarse_levels = nullptr;   // device array of fused coarse-level descriptors
     int coarse_first = -1, coarse_count = 0;
     // profiling (CUDA events around kernel classes)
-    bool prof_on = false;
-    std::vector<cudaEvent_t> prof_ev[5];     // start/stop pairs per kind
-    size_t prof_used[5] = {0, 0, 0, 0, 0};
-    int64_t prof_count[5] = {0, 0, 0, 0, 0};
-    double prof_ms[5] = {0, 0, 0, 0, 0};
+    int prof_on = 0;                         // 0 off, 1 kernel classes, 2 + nested break-down (more event records)
+    std::vector<cudaEvent_t> prof_ev[FEDMX_PROF_KINDS];     // start/stop pairs per kind
+    size_t prof_used[FEDMX_PROF_KINDS] = {};
+    int64_t prof_count[FEDMX_PROF_KINDS] = {};
+    double prof_ms[FEDMX_PROF_KINDS] = {};
     // comm
     void *nccl_comm = nullptr;
     int n_ranks = 1, rank = 0;

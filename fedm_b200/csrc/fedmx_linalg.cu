@@ -220,11 +220,14 @@ __global__ void __launch_bounds__(kRedThreads) finish_reduce_kernel(const double
     if (threadIdx.x == 0) out[j] = r;
 }
 
-// w -= sum_{j<J} h[j0+j] V_{j0+j} ; if NORM: partial[blockIdx] = chunk of ||w_new||^2
-template <int J, bool NORM>
+// w -= sum_{j<J} h[j0+j] V_{j0+j} ; if NORM: partial[blockIdx] = chunk of ||w_new||^2 ;
+// if OUT: the result is not written back to w but, scaled, to `out` (the next Krylov basis vector, whose norm the host
+// already knows from ||w||^2 - sum h^2) -- saves the separate normalisation pass and the norm reduction.
+template <int J, bool NORM, bool OUT>
 __global__ void __launch_bounds__(kRedThreads) multiaxpy_kernel(const double *__restrict__ V, int64_t ld, int j0,
                                                                 const double *__restrict__ h, double *__restrict__ w,
-                                                                int64_t n, double *__restrict__ partial) {
+                                                                int64_t n, double *__restrict__ partial,
+                                                                double *__restrict__ out, double scale) {
     __shared__ double smem[32];
     double hs[J];
 #pragma unroll
@@ -240,15 +243,21 @@ __global__ void __launch_bounds__(kRedThreads) multiaxpy_kernel(const double *__
             w0 = fma(-hs[j], __ldcs(vj), w0);
             w1 = fma(-hs[j], __ldcs(vj + stride), w1);
         }
-        w[i] = w0;
-        w[i + stride] = w1;
+        if (OUT) {
+            out[i] = scale * w0;
+            out[i + stride] = scale * w1;
+        } else {
+            w[i] = w0;
+            w[i + stride] = w1;
+        }
         if (NORM) ww = fma(w0, w0, fma(w1, w1, ww));
     }
     for (; i < n; i += stride) {
         double wi = w[i];
 #pragma unroll
         for (int j = 0; j < J; ++j) wi = fma(-hs[j], V[int64_t(j0 + j) * ld + i], wi);
-        w[i] = wi;
+        if (OUT) out[i] = scale * wi;
+        else w[i] = wi;
         if (NORM) ww = fma(wi, wi, ww);
     }
     if (NORM) {
@@ -475,10 +484,10 @@ int fedmx_multidot(fedmx_ctx *ctx, const double *V, int64_t ld, int nvec, const 
     return FEDMX_OK;
 }
 
-template <bool NORM>
+template <bool NORM, bool OUT>
 static void launch_multiaxpy(fedmx_ctx *ctx, int J, unsigned blocks, const double *V, int64_t ld, int j0, const double *h,
-                             double *w, int64_t n) {
-#define MA_CASE(JJ) case JJ: multiaxpy_kernel<JJ, NORM><<<blocks, kRedThreads, 0, ctx->stream>>>(V, ld, j0, h, w, n, ctx->d_red); break;
+                             double *w, int64_t n, double *out = nullptr, double scale = 1.0) {
+#define MA_CASE(JJ) case JJ: multiaxpy_kernel<JJ, NORM, OUT><<<blocks, kRedThreads, 0, ctx->stream>>>(V, ld, j0, h, w, n, ctx->d_red, out, scale); break;
     switch (J) {
         MA_CASE(1) MA_CASE(2) MA_CASE(3) MA_CASE(4) MA_CASE(5) MA_CASE(6) MA_CASE(7) MA_CASE(8)
     }
@@ -493,12 +502,29 @@ int fedmx_multiaxpy_norm(fedmx_ctx *ctx, const double *V, int64_t ld, int nvec, 
     while (j0 < nvec) {
         const int J = nvec - j0 > 8 ? 8 : nvec - j0;
         const bool last = j0 + J >= nvec;
-        if (last) launch_multiaxpy<true>(ctx, J, blocks, V, ld, j0, h_dev, w, n);
-        else launch_multiaxpy<false>(ctx, J, blocks, V, ld, j0, h_dev, w, n);
+        if (last) launch_multiaxpy<true, false>(ctx, J, blocks, V, ld, j0, h_dev, w, n);
+        else launch_multiaxpy<false, false>(ctx, J, blocks, V, ld, j0, h_dev, w, n);
         j0 += J;
     }
     finish_reduce_kernel<<<1, kRedThreads, 0, ctx->stream>>>(ctx->d_red, int(blocks), norm2_dev);
     ctx->launches++;
+    FEDMX_CHECK_CUDA(ctx, cudaGetLastError());
+    return FEDMX_OK;
+}
+
+// out = scale * (w - sum_j h_j V_j): Gram-Schmidt update and normalisation in one pass (w is left untouched when
+// nvec <= 8, otherwise it holds the partially updated vector)
+int fedmx_multiaxpy_scaled(fedmx_ctx *ctx, const double *V, int64_t ld, int nvec, const double *h_dev, double *w, int64_t n,
+                           double *out, double scale) {
+    const unsigned blocks = grid_for(n, kRedThreads * 2);
+    int j0 = 0;
+    while (j0 < nvec) {
+        const int J = nvec - j0 > 8 ? 8 : nvec - j0;
+        const bool last = j0 + J >= nvec;
+        if (last) launch_multiaxpy<false, true>(ctx, J, blocks, V, ld, j0, h_dev, w, n, out, scale);
+        else launch_multiaxpy<false, false>(ctx, J, blocks, V, ld, j0, h_dev, w, n);
+        j0 += J;
+    }
     FEDMX_CHECK_CUDA(ctx, cudaGetLastError());
     return FEDMX_OK;
 }

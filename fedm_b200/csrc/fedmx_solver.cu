@@ -14,6 +14,8 @@
 int fedmx_apply_dinv(fedmx_ctx *ctx, const double *d_r, double *d_z);
 int fedmx_multidot(fedmx_ctx *ctx, const double *V, int64_t ld, int nvec, const double *w, int64_t n, double *out_dev, bool with_ww);
 int fedmx_multiaxpy_norm(fedmx_ctx *ctx, const double *V, int64_t ld, int nvec, const double *h_dev, double *w, int64_t n, double *norm2_dev);
+int fedmx_multiaxpy_scaled(fedmx_ctx *ctx, const double *V, int64_t ld, int nvec, const double *h_dev, double *w, int64_t n,
+                           double *out, double scale);
 int fedmx_scale_copy(fedmx_ctx *ctx, const double *x, double *y, int64_t n, double alpha, const double *inv_of_dev);
 int fedmx_combine(fedmx_ctx *ctx, const double *V, int64_t ld, int nvec, const double *c_dev, double *x, int64_t n, double sign);
 int fedmx_axpy(fedmx_ctx *ctx, double alpha, const double *x, double *y, int64_t n);
@@ -66,21 +68,37 @@ int gmres_impl(fedmx_ctx *ctx, const double *d_b, double *d_x, int restart, doub
             } else {
                 if ((rc = fedmx_two_stage_after_spmv(ctx, Vk, w))) return rc;
             }
+            // Classical Gram-Schmidt with ONE reduction per iteration: h = V^T w and ||w||^2 come out of the same pass (and
+            // the same allreduce); the norm of the orthogonalised vector follows from Pythagoras,
+            // ||w - V h||^2 = ||w||^2 - |h|^2, so the update pass can normalise and write V_{k+1} directly.  When that
+            // difference cancels (new direction almost inside the Krylov space: near convergence / breakdown) the norm
+            // is recomputed explicitly as PETSc does.
+            double hk1;
             {
                 ProfScope prof(ctx, FEDMX_PROF_ORTHO);
-                if ((rc = fedmx_multidot(ctx, V, ld, k + 1, w, n, dh, false))) return rc;
-                if (multi && (rc = fedmx_global_sum(ctx, dh, k + 1))) return rc;
-                if ((rc = fedmx_multiaxpy_norm(ctx, V, ld, k + 1, dh, w, n, dh + 64))) return rc;
-                if (multi && (rc = fedmx_global_sum(ctx, dh + 64, 1))) return rc;
+                if ((rc = fedmx_multidot(ctx, V, ld, k + 1, w, n, dh, true))) return rc;
+                if (multi && (rc = fedmx_global_sum(ctx, dh, k + 2))) return rc;
+                FEDMX_CHECK_CUDA(ctx, cudaMemcpyAsync(hp, dh, (k + 2) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+                FEDMX_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                FEDMX_REQUIRE(ctx, !(ctx->peer.h_err && *ctx->peer.h_err), "peer-memory collective timed out waiting for a neighbour's flag");
+                double hh = 0.0;
+                for (int i = 0; i <= k; ++i) hh += hp[i] * hp[i];
+                const double ww = hp[k + 1], nrm2 = ww - hh;
+                if (nrm2 > 1e-2 * ww) {
+                    hk1 = sqrt(nrm2);
+                    if ((rc = fedmx_multiaxpy_scaled(ctx, V, ld, k + 1, dh, w, n, V + int64_t(k + 1) * ld, 1.0 / hk1))) return rc;
+                } else {
+                    if ((rc = fedmx_multiaxpy_norm(ctx, V, ld, k + 1, dh, w, n, dh + 64))) return rc;
+                    if (multi && (rc = fedmx_global_sum(ctx, dh + 64, 1))) return rc;
+                    FEDMX_CHECK_CUDA(ctx, cudaMemcpyAsync(hp + 64, dh + 64, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+                    FEDMX_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                    hk1 = sqrt(hp[64]);
+                    // next basis vector: V_{k+1} = w / ||w||
+                    if (hk1 > 0.0 && (rc = fedmx_scale_copy(ctx, w, V + int64_t(k + 1) * ld, n, 1.0 / hk1, nullptr))) return rc;
+                }
             }
-            FEDMX_CHECK_CUDA(ctx, cudaMemcpyAsync(hp, dh, 65 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-            FEDMX_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            FEDMX_REQUIRE(ctx, !(ctx->peer.h_err && *ctx->peer.h_err), "peer-memory collective timed out waiting for a neighbour's flag");
-            const double hk1 = sqrt(hp[64]);
             for (int i = 0; i <= k; ++i) Hm(i, k) = hp[i];
             Hm(k + 1, k) = hk1;
-            // next basis vector: V_{k+1} = w / ||w||  (one pass, after the norm has reached the host)
-            if (hk1 > 0.0 && (rc = fedmx_scale_copy(ctx, w, V + int64_t(k + 1) * ld, n, 1.0 / hk1, nullptr))) return rc;
             for (int i = 0; i < k; ++i) {
                 const double t = cs[i] * Hm(i, k) + sn[i] * Hm(i + 1, k);
                 Hm(i + 1, k) = -sn[i] * Hm(i, k) + cs[i] * Hm(i + 1, k);

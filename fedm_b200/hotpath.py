@@ -281,12 +281,14 @@ class HotPath:
         return int(self.lib.fedmx_launch_count(self.h, 1 if reset else 0))
 
     def profile_enable(self, on=True):
-        self._ck(self.lib.fedmx_profile_enable(self.h, 1 if on else 0))
+        """on: False/0 off, True/1 kernel classes, 2 = plus the nested multigrid-level / collective break-down."""
+        self._ck(self.lib.fedmx_profile_enable(self.h, int(on)))
 
     def profile_get(self):
         """{kind: (launches, total_ms)} since the last call, per kernel class (CUDA events on the stream)."""
         out = {}
-        for kind, name in enumerate(("assemble_jacobian", "assemble_residual", "spmv", "orthogonalisation", "preconditioner")):
+        for kind, name in enumerate(("assemble_jacobian", "assemble_residual", "spmv", "orthogonalisation", "preconditioner",
+                                     "mg_fine", "mg_mid", "mg_coarse", "comm")):
             n, ms = C.c_int64(), C.c_double()
             self._ck(self.lib.fedmx_profile_get(self.h, kind, C.byref(n), C.byref(ms)))
             out[name] = (n.value, ms.value)

@@ -241,7 +241,10 @@ int64_t fedmx_launch_count(fedmx_ctx *ctx, int reset);
  * 3 = Gram-Schmidt multi-dot + multi-axpy, 4 = two-stage preconditioner (block Jacobi + AMG V-cycle).  fedmx_profile_get synchronises, returns launches and total ms
  * since the last reset and resets the class. */
 enum { FEDMX_PROF_ASM_JAC = 0, FEDMX_PROF_ASM_RES = 1, FEDMX_PROF_SPMV = 2, FEDMX_PROF_ORTHO = 3, FEDMX_PROF_PRECOND = 4,
-       FEDMX_PROF_KINDS = 5 };
+       /* finer break-down (nested inside the classes above): multigrid finest level / separately launched coarser
+        * levels / cluster-fused coarsest levels, and the collectives (halo exchanges + allreduces) */
+       FEDMX_PROF_MG_FINE = 5, FEDMX_PROF_MG_MID = 6, FEDMX_PROF_MG_COARSE = 7, FEDMX_PROF_COMM = 8,
+       FEDMX_PROF_KINDS = 9 };
 int fedmx_profile_enable(fedmx_ctx *ctx, int on);
 int fedmx_profile_get(fedmx_ctx *ctx, int kind, int64_t *count, double *total_ms);
 
