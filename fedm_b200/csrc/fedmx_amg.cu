@@ -436,7 +436,11 @@ extern "C" int fedmx_amg_add_level(fedmx_ctx *ctx, int64_t n, const double *h_di
     if ((rc = fedmx_upload(ctx, &lv.dinv, d))) return rc;
     // the finest level of a partitioned run carries ghost entries (columns of A beyond the owned rows)
     const int64_t nvec = ctx->amg_levels.empty() ? std::max<int64_t>(n, ctx->n_vertices) : n;
-    if ((rc = fedmx_dev_alloc(ctx, &lv.b, nvec))) return rc;
+    // level 1 of a partitioned run: the restricted residual is summed over the ranks -- produce it directly in the peer
+    // heap's allreduce buffer (no staging copy)
+    double *heap_b = (ctx->n_ranks > 1 && ctx->amg_levels.size() == 1) ? fedmx_peer_big_buffer(ctx, n) : nullptr;
+    if (heap_b) lv.b = heap_b;
+    else if ((rc = fedmx_dev_alloc(ctx, &lv.b, nvec))) return rc;
     if ((rc = fedmx_dev_alloc(ctx, &lv.x, nvec))) return rc;
     if ((rc = fedmx_dev_alloc(ctx, &lv.x2, nvec))) return rc;
     if ((rc = fedmx_dev_alloc(ctx, &lv.r, nvec))) return rc;

@@ -218,3 +218,4 @@ int fedmx_precond_apply(fedmx_ctx *ctx, const double *d_r, double *d_z);
 int fedmx_peer_halo_exchange(fedmx_ctx *ctx, double *d_vec, int n_comp);
 int fedmx_peer_allreduce(fedmx_ctx *ctx, double *d_buf, int64_t n);
 int fedmx_peer_destroy(fedmx_ctx *ctx);
+double *fedmx_peer_big_buffer(fedmx_ctx *ctx, int64_t n);

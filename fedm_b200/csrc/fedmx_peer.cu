@@ -140,21 +140,23 @@ struct BigArgs {
     unsigned long long *flags[FEDMX_MAX_RANKS];       // peer r's big flag of this rank
     const unsigned long long *my_flags;
     const double *my_out;
-    unsigned long long epoch;
+    unsigned long long epoch_ready, epoch;            // "my input is complete" / "my chunk is in your output"
     unsigned int *counter;
     int *err;
 };
 
-__global__ void big_barrier_kernel(BigArgs a) {
-    const int t = threadIdx.x;
-    __threadfence_system();
-    if (t < a.n_ranks) {
-        st_release_sys(a.flags[t], a.epoch);
-        spin_until(a.my_flags + t, a.epoch, a.err);
-    }
-}
-
 __global__ void __launch_bounds__(256) big_reduce_push_kernel(BigArgs a) {
+    // barrier: my input (written by the preceding kernel of this stream) is complete -> tell every peer, then wait until
+    // every peer's input is complete.  All blocks of the (<= 148-block) grid are co-resident, so spinning is safe.
+    __shared__ int ok;
+    if (threadIdx.x == 0) ok = 1;
+    __syncthreads();
+    if (threadIdx.x < a.n_ranks) {
+        if (blockIdx.x == 0) { __threadfence_system(); st_release_sys(a.flags[threadIdx.x], a.epoch_ready); }
+        if (!spin_until(a.my_flags + threadIdx.x, a.epoch_ready, a.err)) ok = 0;
+    }
+    __syncthreads();
+    if (!ok) return;
     const long long chunk = (a.n + a.n_ranks - 1) / a.n_ranks;
     const long long lo = chunk * a.rank, hi = min(a.n, lo + chunk);
     for (long long i = lo + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < hi; i += (long long)gridDim.x * blockDim.x) {
@@ -361,16 +363,23 @@ int fedmx_peer_allreduce(fedmx_ctx *ctx, double *d_buf, int64_t n) {
     a.my_out = (const double *)(P.base + P.off_big_out);
     a.counter = P.d_counter + 1;
     a.err = P.d_err;
-    FEDMX_CHECK_CUDA(ctx, cudaMemcpyAsync(P.base + P.off_big_in, d_buf, size_t(n) * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-    a.epoch = ++P.big_epoch;
-    big_barrier_kernel<<<1, 32, 0, ctx->stream>>>(a);
+    if ((const char *)d_buf != P.base + P.off_big_in)      // callers that produce their vector in the heap skip the copy
+        FEDMX_CHECK_CUDA(ctx, cudaMemcpyAsync(P.base + P.off_big_in, d_buf, size_t(n) * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    a.epoch_ready = ++P.big_epoch;
     a.epoch = ++P.big_epoch;
     const long long chunk = (n + ctx->n_ranks - 1) / ctx->n_ranks;
     const unsigned b1 = unsigned(std::min<long long>(148, std::max<long long>(1, (chunk + 255) / 256)));
     big_reduce_push_kernel<<<b1, 256, 0, ctx->stream>>>(a);
     const unsigned b2 = unsigned(std::min<long long>(296, std::max<long long>(1, (n + 255) / 256)));
     big_wait_copy_kernel<<<b2, 256, 0, ctx->stream>>>(d_buf, a);
-    ctx->launches += 3;
+    ctx->launches += 2;
     FEDMX_CHECK_CUDA(ctx, cudaGetLastError());
     return FEDMX_OK;
+}
+
+// Input buffer of the big allreduce: a vector produced directly here is reduced without a staging copy.
+double *fedmx_peer_big_buffer(fedmx_ctx *ctx, int64_t n) {
+    PeerState &P = ctx->peer;
+    if (!P.opened || n > P.big_cap) return nullptr;
+    return (double *)(P.base + P.off_big_in);
 }

@@ -72,7 +72,10 @@ int gmres_impl(fedmx_ctx *ctx, const double *d_b, double *d_x, int restart, doub
             // the same allreduce); the norm of the orthogonalised vector follows from Pythagoras,
             // ||w - V h||^2 = ||w||^2 - |h|^2, so the update pass can normalise and write V_{k+1} directly.  When that
             // difference cancels (new direction almost inside the Krylov space: near convergence / breakdown) the norm
-            // is recomputed explicitly as PETSc does.
+            // is recomputed explicitly as PETSc does.  The shortcut inherits classical Gram-Schmidt's loss of orthogonality
+            // (its error is O(|V^T V - I|) ||w||^2), which costs extra iterations once the residual is driven far down
+            // (measured: 54 -> 72-83 iterations at rtol 1e-13), so it is only taken for the loose tolerances of the
+            // reference's iterative mode (rtol 1e-5); tight "direct-solver" runs use the explicit norm throughout.
             double hk1;
             {
                 ProfScope prof(ctx, FEDMX_PROF_ORTHO);
@@ -84,7 +87,7 @@ int gmres_impl(fedmx_ctx *ctx, const double *d_b, double *d_x, int restart, doub
                 double hh = 0.0;
                 for (int i = 0; i <= k; ++i) hh += hp[i] * hp[i];
                 const double ww = hp[k + 1], nrm2 = ww - hh;
-                if (nrm2 > 1e-2 * ww) {
+                if (rtol >= 1e-8 && nrm2 > 1e-2 * ww) {
                     hk1 = sqrt(nrm2);
                     if ((rc = fedmx_multiaxpy_scaled(ctx, V, ld, k + 1, dh, w, n, V + int64_t(k + 1) * ld, 1.0 / hk1))) return rc;
                 } else {
