@@ -31,6 +31,7 @@ namespace {
 // =====================================================================================================
 struct StreamerModel {
     static constexpr int MINB = 2, MINB_RES = 4;
+    static constexpr unsigned ZERO_MASK = 1u << 3;      // d R_e / d U_i == 0: the electron equation does not see the ions
     static constexpr int NEQ = 3;
     static constexpr int NF = 2;
     static constexpr int NC = 2;      // nodal c_s = exp(u_s/6): e^{u(q)} at the 3-point rule is a product of them
@@ -190,6 +191,7 @@ struct StreamerModel {
 // =====================================================================================================
 struct PoissonModel {
     static constexpr int MINB = 2, MINB_RES = 2;
+    static constexpr unsigned ZERO_MASK = 0;
     static constexpr int NC = 0;
     static constexpr int NEQ = 1;
     static constexpr int NF = 2;
@@ -237,6 +239,7 @@ struct PoissonModel {
 // =====================================================================================================
 struct TofModel {
     static constexpr int MINB = 2, MINB_RES = 2;
+    static constexpr unsigned ZERO_MASK = 0;
     static constexpr int NC = 0;
     static constexpr int NEQ = 1;
     static constexpr int NF = 1;
@@ -307,6 +310,7 @@ struct TofModel {
 // =====================================================================================================
 struct ProjectionModel {
     static constexpr int MINB = 2, MINB_RES = 2;
+    static constexpr unsigned ZERO_MASK = 0;
     static constexpr int NC = 0;
     static constexpr int NEQ = 1;
     static constexpr int NF = 1;
@@ -455,13 +459,15 @@ extern "C" int fedmx_model_set(fedmx_ctx *ctx, int model_id, int n_params, const
     if (!ctx) return FEDMX_EINVAL;
     FEDMX_REQUIRE(ctx, n_params >= 0 && n_params <= FEDMX_MAX_PARAMS, "fedmx_model_set: too many parameters");
     int neq = 0, nf = 0;
+    unsigned zmask = 0;
     if (model_id == FEDMX_MODEL_PLUGIN) {
+        ctx->zero_mask = 0;
         FEDMX_REQUIRE(ctx, ctx->plugin_launch, "fedmx_model_set: load the plug-in first (fedmx_plugin_load)");
         for (int i = 0; i < FEDMX_MAX_PARAMS; ++i) ctx->mp.p[i] = i < n_params ? h_params[i] : 0.0;
         return FEDMX_OK;
     }
     switch (model_id) {
-        case FEDMX_MODEL_STREAMER: neq = StreamerModel::NEQ; nf = StreamerModel::NF; break;
+        case FEDMX_MODEL_STREAMER: neq = StreamerModel::NEQ; nf = StreamerModel::NF; zmask = StreamerModel::ZERO_MASK; break;
         case FEDMX_MODEL_POISSON: neq = PoissonModel::NEQ; nf = PoissonModel::NF; break;
         case FEDMX_MODEL_TOF: neq = TofModel::NEQ; nf = TofModel::NF; break;
         case FEDMX_MODEL_GLOW: neq = GlowModel::NEQ; nf = GlowModel::NF; break;
@@ -474,6 +480,7 @@ extern "C" int fedmx_model_set(fedmx_ctx *ctx, int model_id, int n_params, const
     ctx->mp.model_id = model_id;
     ctx->mp.n_eq = neq;
     ctx->mp.n_fields = nf;
+    ctx->zero_mask = zmask;
     for (int i = 0; i < FEDMX_MAX_PARAMS; ++i) ctx->mp.p[i] = i < n_params ? h_params[i] : 0.0;
     return FEDMX_OK;
 }

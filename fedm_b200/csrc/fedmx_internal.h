@@ -123,6 +123,7 @@ struct fedmx_ctx {
     double *d_dinv = nullptr;    // [n_slices*32 * NB] entry-major per slice
     // model
     ModelParams mp{};
+    unsigned zero_mask = 0;      // structurally zero block entries of the model (never written, skipped by the SpMV)
     const double *d_fields = nullptr;
     // run-time compiled model (form compiler plug-in)
     void *plugin_handle = nullptr;

@@ -43,7 +43,8 @@ __device__ __forceinline__ double block_sum(double v, double *smem) {
 template <int NEQ, bool PRECOND, bool EXTRACT>
 __global__ void __launch_bounds__(128) spmv_kernel(SellView S, const double *__restrict__ val,
                                                    const double *__restrict__ dinv, const double *__restrict__ x,
-                                                   double *__restrict__ y, int comp, double *__restrict__ rhs_c) {
+                                                   double *__restrict__ y, int comp, double *__restrict__ rhs_c,
+                                                   unsigned zmask) {
     constexpr int NB = NEQ * NEQ;
     const int64_t row = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     const int64_t s = row / FEDMX_SLICE;
@@ -64,7 +65,8 @@ __global__ void __launch_bounds__(128) spmv_kernel(SellView S, const double *__r
 #pragma unroll
         for (int i = 0; i < NEQ; ++i)
 #pragma unroll
-            for (int l = 0; l < NEQ; ++l) acc[i] = fma(__ldcs(v + (i * NEQ + l) * FEDMX_SLICE), xc[l], acc[i]);
+            for (int l = 0; l < NEQ; ++l)
+                if (!((zmask >> (i * NEQ + l)) & 1u)) acc[i] = fma(__ldcs(v + (i * NEQ + l) * FEDMX_SLICE), xc[l], acc[i]);
     }
     if (row >= S.n_rows) return;
     if (EXTRACT) {
@@ -424,9 +426,9 @@ int fedmx_spmv_precond(fedmx_ctx *ctx, const double *d_x, double *d_y, bool prec
     FEDMX_REQUIRE(ctx, !d_rhs_c || precond, "spmv: component extraction is only built for the preconditioned variant");
 #define SPMV_CASE(N)                                                                                              \
     case N:                                                                                                       \
-        if (d_rhs_c) spmv_kernel<N, true, true><<<blocks, threads, 0, ctx->stream>>>(ctx->sell, ctx->d_val, ctx->d_dinv, d_x, d_y, comp, d_rhs_c); \
-        else if (precond) spmv_kernel<N, true, false><<<blocks, threads, 0, ctx->stream>>>(ctx->sell, ctx->d_val, ctx->d_dinv, d_x, d_y, 0, nullptr); \
-        else spmv_kernel<N, false, false><<<blocks, threads, 0, ctx->stream>>>(ctx->sell, ctx->d_val, ctx->d_dinv, d_x, d_y, 0, nullptr);        \
+        if (d_rhs_c) spmv_kernel<N, true, true><<<blocks, threads, 0, ctx->stream>>>(ctx->sell, ctx->d_val, ctx->d_dinv, d_x, d_y, comp, d_rhs_c, ctx->zero_mask); \
+        else if (precond) spmv_kernel<N, true, false><<<blocks, threads, 0, ctx->stream>>>(ctx->sell, ctx->d_val, ctx->d_dinv, d_x, d_y, 0, nullptr, ctx->zero_mask); \
+        else spmv_kernel<N, false, false><<<blocks, threads, 0, ctx->stream>>>(ctx->sell, ctx->d_val, ctx->d_dinv, d_x, d_y, 0, nullptr, ctx->zero_mask);        \
         break;
     switch (ctx->n_eq) {
         SPMV_CASE(1)

@@ -23,6 +23,7 @@
 
 struct GlowModel {
     static constexpr int MINB = 2, MINB_RES = 2;
+    static constexpr unsigned ZERO_MASK = 0;
     static constexpr int NC = 0;
     static constexpr int NEQ = 5;
     static constexpr int NF = 28;

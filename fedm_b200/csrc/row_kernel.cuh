@@ -66,22 +66,27 @@ struct RowOut {
 // =====================================================================================================
 // Generic row kernel
 // =====================================================================================================
-template <int NEQ>
+// ZMASK: bit e set = entry e of every block is structurally zero for this model (e.g. d R_e / d U_i of the streamer
+// system).  dolfin keeps such entries in the pattern and so does the exported pattern, but they are never written (the
+// value array is zero-initialised once) and the SpMV skips them: 1/9 less matrix traffic for the streamer model.
+template <int NEQ, unsigned ZMASK>
 __device__ __forceinline__ void store_block(const AsmArgs &A, int64_t group_base, int slot, int lane, const double *blk) {
     constexpr int NB = NEQ * NEQ;
     const int64_t g = group_base + int64_t(slot) * FEDMX_SLICE;
     double *dst = A.val + g * NB + lane;
 #pragma unroll
-    for (int e = 0; e < NB; ++e) dst[e * FEDMX_SLICE] = blk[e];
+    for (int e = 0; e < NB; ++e)
+        if (!((ZMASK >> e) & 1u)) dst[e * FEDMX_SLICE] = blk[e];
 }
 
-template <int NEQ>
+template <int NEQ, unsigned ZMASK>
 __device__ __forceinline__ void add_block(const AsmArgs &A, int64_t group_base, int slot, int lane, const double *blk) {
     constexpr int NB = NEQ * NEQ;
     const int64_t g = group_base + int64_t(slot) * FEDMX_SLICE;
     double *dst = A.val + g * NB + lane;
 #pragma unroll
-    for (int e = 0; e < NB; ++e) dst[e * FEDMX_SLICE] += blk[e];
+    for (int e = 0; e < NB; ++e)
+        if (!((ZMASK >> e) & 1u)) dst[e * FEDMX_SLICE] += blk[e];
 }
 
 // Zero block row `comp` with static register indices (comp is a run-time value: a dynamic index would push the
@@ -98,6 +103,7 @@ __device__ __forceinline__ void zero_row(double *blk, int comp) {
 template <class Model, bool JAC, int MINB>
 __global__ void __launch_bounds__(128, MINB) assemble_rows_kernel(AsmArgs A) {
     constexpr int NEQ = Model::NEQ, NF = Model::NF, NC = Model::NC, NB = NEQ * NEQ;
+    constexpr unsigned ZMASK = Model::ZERO_MASK;
     const int64_t row = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     const int64_t s = row / FEDMX_SLICE;
     const int lane = int(row % FEDMX_SLICE);
@@ -156,13 +162,13 @@ __global__ void __launch_bounds__(128, MINB) assemble_rows_kernel(AsmArgs A) {
             for (int q = 0; q < NB; ++q) carry[q] += o.J[1][q];
             if (bc) zero_row<NEQ>(carry, bc_comp);
             // block (i, vp) is complete (or the partial first block of a closed fan): write it
-            store_block<NEQ>(A, gbase, PACK_SLOT_P(pack), lane, carry);
+            store_block<NEQ, ZMASK>(A, gbase, PACK_SLOT_P(pack), lane, carry);
 #pragma unroll
             for (int q = 0; q < NB; ++q) carry[q] = o.J[2][q];
             if (PACK_LAST(pack)) {
                 if (bc) zero_row<NEQ>(carry, bc_comp);
-                if (PACK_CLOSED(pack)) add_block<NEQ>(A, gbase, PACK_SLOT_N(pack), lane, carry);
-                else store_block<NEQ>(A, gbase, PACK_SLOT_N(pack), lane, carry);
+                if (PACK_CLOSED(pack)) add_block<NEQ, ZMASK>(A, gbase, PACK_SLOT_N(pack), lane, carry);
+                else store_block<NEQ, ZMASK>(A, gbase, PACK_SLOT_N(pack), lane, carry);
             }
         }
         if (has1) {
@@ -185,7 +191,7 @@ __global__ void __launch_bounds__(128, MINB) assemble_rows_kernel(AsmArgs A) {
                 if (k == bc_comp) diag[k * NEQ + k] = 1.0;
         }
     }
-    if (JAC) store_block<NEQ>(A, gbase, diag_slot, lane, diag);
+    if (JAC) store_block<NEQ, ZMASK>(A, gbase, diag_slot, lane, diag);
     if (A.res) {
 #pragma unroll
         for (int k = 0; k < NEQ; ++k) A.res[int64_t(NEQ) * row + k] = R[k];

@@ -347,6 +347,7 @@ class CompiledForm:
             L.append(f"static __device__ __forceinline__ double interp_fn{k}(double X0, double X1, const ModelParams &mp) {{ return {_plain_code(ip.expr, self)}; }}")
         L.append("struct JitModel {")
         L.append("    static constexpr int MINB = 2, MINB_RES = 2;")
+        L.append("    static constexpr unsigned ZERO_MASK = 0;")
         L.append(f"    static constexpr int NEQ = {neq};\n    static constexpr int NF = {nf};\n    static constexpr int NC = 0;")
         L.append(f"    typedef Dual<{nd}> D;\n    typedef Vtx<{neq}, {nf}, 0> V;")
         L.append("    template <bool JAC>")
