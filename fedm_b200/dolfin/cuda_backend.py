@@ -17,7 +17,8 @@ class TorchStore:
         return self.t.cpu().numpy()
 
     def set_numpy(self, arr):
-        self.t.copy_(torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float64)))
+        a = np.ascontiguousarray(arr, dtype=np.float64)
+        self.t.copy_(torch.from_numpy(a if a.flags.writeable else a.copy()))
 
     def size(self):
         return self.t.numel()

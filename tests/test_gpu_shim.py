@@ -52,3 +52,24 @@ def test_time_of_flight_script_on_gpu_matches_fenics_golden(cuda_shim, tmp_path,
     assert np.abs(vals - gold).max() <= 1e-9 * gold.max()
     ref = float((golden_dir / "time_of_flight_relative_error.log").read_text().split("=")[-1])
     assert abs(rel - ref) <= 1e-8 * ref
+
+
+def test_glow_discharge_script_on_gpu_matches_fenics_golden(cuda_shim, tmp_path, golden_dir):
+    """The full multi-species configuration through the public API: input-deck readers, Source_term / Energy_Source_term,
+    semi-implicit coefficients, 'flux source' boundary terms with secondary emission, table interpolation, project(),
+    adaptive_solver + PID controller and the checkpoint writer; the 5-equation form is JIT-compiled into one row kernel.
+    Compared with the reference's golden HDF5 fields and error log (6 accepted steps to t = 1e-11)."""
+    import glow_discharge as gd
+    u, info = gd.main(input_dir=golden_dir / "glow_discharge_input", output_dir=tmp_path)
+    rows = [[float(v) for v in ln.split()] for ln in (tmp_path / "relative error.log").read_text().splitlines()]
+    gold = [[float(v) for v in ln.split()] for ln in (golden_dir / "glow_discharge_relative_error.log").read_text().splitlines()]
+    assert len(rows) == 6
+    for (e, dto, dt), (ge, gdto, gdt) in zip(rows, gold):
+        assert abs(e - ge) <= 1e-7 * ge and abs(dt - gdt) <= 1e-8 * gdt
+    g = np.load(golden_dir / "glow_h5.npz")
+    d2v = np.empty(20201, dtype=np.int64)
+    d2v[g["cell_dofs"]] = g["topology"].ravel()
+    for name in ("electrons", "Ar_plus", "Ar_star"):
+        z = np.load(tmp_path / "number density" / name / f"{name}.npz")
+        ref = g[name + "_1"]
+        assert np.abs((z[f"{name}_1"][d2v] - ref) / ref).max() <= 1e-8, name
