@@ -485,6 +485,12 @@ extern "C" int fedmx_model_set(fedmx_ctx *ctx, int model_id, int n_params, const
     return FEDMX_OK;
 }
 
+extern "C" int fedmx_ident_zeros_set(fedmx_ctx *ctx, int on) {
+    if (!ctx) return FEDMX_EINVAL;
+    ctx->mp.ident_zeros = on != 0;
+    return FEDMX_OK;
+}
+
 extern "C" int fedmx_fields_bind(fedmx_ctx *ctx, int n_fields, const double *d_fields) {
     if (!ctx) return FEDMX_EINVAL;
     FEDMX_REQUIRE(ctx, ctx->mp.model_id != 0, "fedmx_fields_bind: set the model first");

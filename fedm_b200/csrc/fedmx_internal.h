@@ -59,6 +59,8 @@ struct ModelParams {
     double p[FEDMX_MAX_PARAMS];
     double bc_values[FEDMX_MAX_BC];
     double dt, dt_old, t;
+    int ident_zeros;             // dolfin's A.ident_zeros(): an all-zero matrix row gets a unit diagonal
+    int pad_;
 };
 
 // Scalar SELL-32 matrix (multigrid operators): entry (row r = 32 s + l, k) at slice_ptr[s] + 32 k + l

@@ -410,7 +410,9 @@ int fedmx_update_block_jacobi(fedmx_ctx *ctx) {
     const unsigned blocks = unsigned((ctx->sell.n_slices * FEDMX_SLICE + threads - 1) / threads);
     switch (ctx->n_eq) {
         case 1: block_jacobi_kernel<1><<<blocks, threads, 0, ctx->stream>>>(ctx->sell, ctx->d_val, ctx->d_dinv); break;
+        case 2: block_jacobi_kernel<2><<<blocks, threads, 0, ctx->stream>>>(ctx->sell, ctx->d_val, ctx->d_dinv); break;
         case 3: block_jacobi_kernel<3><<<blocks, threads, 0, ctx->stream>>>(ctx->sell, ctx->d_val, ctx->d_dinv); break;
+        case 4: block_jacobi_kernel<4><<<blocks, threads, 0, ctx->stream>>>(ctx->sell, ctx->d_val, ctx->d_dinv); break;
         case 5: block_jacobi_kernel<5><<<blocks, threads, 0, ctx->stream>>>(ctx->sell, ctx->d_val, ctx->d_dinv); break;
         default: ctx->err = "block Jacobi: unsupported n_eq"; return FEDMX_EUNSUPPORTED;
     }
@@ -432,7 +434,9 @@ int fedmx_spmv_precond(fedmx_ctx *ctx, const double *d_x, double *d_y, bool prec
         break;
     switch (ctx->n_eq) {
         SPMV_CASE(1)
+        SPMV_CASE(2)
         SPMV_CASE(3)
+        SPMV_CASE(4)
         SPMV_CASE(5)
         default: ctx->err = "spmv: unsupported n_eq"; return FEDMX_EUNSUPPORTED;
     }
@@ -447,7 +451,9 @@ int fedmx_apply_dinv(fedmx_ctx *ctx, const double *d_r, double *d_z) {
     const unsigned blocks = unsigned((ctx->n_owned + threads - 1) / threads);
     switch (ctx->n_eq) {
         case 1: apply_dinv_kernel<1><<<blocks, threads, 0, ctx->stream>>>(ctx->sell, ctx->d_dinv, d_r, d_z); break;
+        case 2: apply_dinv_kernel<2><<<blocks, threads, 0, ctx->stream>>>(ctx->sell, ctx->d_dinv, d_r, d_z); break;
         case 3: apply_dinv_kernel<3><<<blocks, threads, 0, ctx->stream>>>(ctx->sell, ctx->d_dinv, d_r, d_z); break;
+        case 4: apply_dinv_kernel<4><<<blocks, threads, 0, ctx->stream>>>(ctx->sell, ctx->d_dinv, d_r, d_z); break;
         case 5: apply_dinv_kernel<5><<<blocks, threads, 0, ctx->stream>>>(ctx->sell, ctx->d_dinv, d_r, d_z); break;
         default: ctx->err = "apply_dinv: unsupported n_eq"; return FEDMX_EUNSUPPORTED;
     }

@@ -191,6 +191,19 @@ __global__ void __launch_bounds__(128, MINB) assemble_rows_kernel(AsmArgs A) {
                 if (k == bc_comp) diag[k * NEQ + k] = 1.0;
         }
     }
+    if (JAC && A.mp.ident_zeros) {
+        // ident_zeros (fedm/functions.py:1147, Normal_vector): rows without any contribution -- forms that live on the
+        // boundary only -- become identity rows.  Mass-type forms: the row is zero iff its diagonal block row is zero.
+#pragma unroll
+        for (int k = 0; k < NEQ; ++k) {
+            bool zero = true;
+#pragma unroll
+            for (int l = 0; l < NEQ; ++l) zero = zero && diag[k * NEQ + l] == 0.0;
+#pragma unroll
+            for (int l = 0; l < NEQ; ++l)
+                if (l == k && zero) diag[k * NEQ + l] = 1.0;
+        }
+    }
     if (JAC) store_block<NEQ, ZMASK>(A, gbase, diag_slot, lane, diag);
     if (A.res) {
 #pragma unroll

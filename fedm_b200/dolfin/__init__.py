@@ -283,6 +283,8 @@ class _Indexable:
         return iter(self._args)
 
     def ufl_expr(self):
+        if self.space.vector and self.space.n_comp == 2:
+            return _ufl.Vec(self._args[0], self._args[1])
         if self.space.n_comp != 1:
             raise TypeError("a mixed trial/test function must be indexed")
         return self._args[0]
@@ -603,15 +605,28 @@ class DirichletBC:
             self.space, self.comp = space, 0
         self.value = value
         tri = self.space.mesh().tri
-        fv = tri.exterior_facets()
         xy = tri.coords
         inside = where.inside if isinstance(where, SubDomain) else where
+        # dolfin's "topological" search visits every facet of the mesh (on_boundary = the facet is exterior); interior
+        # facets only matter for sub-domains that ignore on_boundary (BoundaryGradient's zeroDomain), so they are only
+        # walked when an interior probe point is inside
+        ext = tri.exterior_facets()
+        facets = [(ext, True)]
+        probes = range(0, tri.num_cells, max(1, tri.num_cells // 64))
+        if any(bool(inside(xy[tri.cells[c]].mean(axis=0), False)) for c in probes):
+            c = tri.cells.astype(np.int64)
+            edges = np.vstack((c[:, (0, 1)], c[:, (1, 2)], c[:, (0, 2)]))
+            edges.sort(axis=1)
+            key, counts = np.unique(edges[:, 0] * tri.num_vertices + edges[:, 1], return_counts=True)
+            ikey = key[counts == 2]
+            facets.append((np.stack((ikey // tri.num_vertices, ikey % tri.num_vertices), axis=1), False))
         nodes = set()
-        for a, b in fv:
-            pa, pb = xy[a], xy[b]
-            if inside(pa, True) and inside(pb, True) and inside(0.5 * (pa + pb), True):
-                nodes.add(int(a))
-                nodes.add(int(b))
+        for fv, on_boundary in facets:
+            for a, b in fv:
+                pa, pb = xy[a], xy[b]
+                if inside(pa, on_boundary) and inside(pb, on_boundary) and inside(0.5 * (pa + pb), on_boundary):
+                    nodes.add(int(a))
+                    nodes.add(int(b))
         self.nodes = np.array(sorted(nodes), dtype=np.int32)
 
     def current_value(self):
@@ -632,10 +647,10 @@ class DirichletBC:
 # ---- assemble / solve ---------------------------------------------------------------------------------------------------
 class _LazyMatrix:
     def __init__(self, form):
-        self.form, self.bcs = form, []
+        self.form, self.bcs, self.ident = form, [], False
 
     def ident_zeros(self):
-        pass
+        self.ident = True
 
 
 class _LazyVector(GenericVector):
@@ -656,9 +671,9 @@ def _quadrature_degree():
     return None if q in (None, -1, "auto") else int(q)
 
 
-def _solve_linear(a_form, L_form, u, bcs, tight=True):
+def _solve_linear(a_form, L_form, u, bcs, tight=True, ident_zeros=False):
     residual = action(a_form, u) - L_form
-    prob = get_backend().compile(residual, u, bcs, _quadrature_degree())
+    prob = get_backend().compile(residual, u, bcs, _quadrature_degree(), ident_zeros=ident_zeros)
     prob.solve_newton(u, rtol=1e-12, atol=0.0, max_it=3, linear_solver="mumps", raise_on_failure=False)
 
 
@@ -669,7 +684,7 @@ def solve(A, x, b, *args):
     if u is None:
         raise NotImplementedError("solve(A, x, b): x must be the vector of a Function")
     bcs = list({id(bc): bc for bc in A.bcs + b.bcs}.values())
-    _solve_linear(A.form, b.form, u, bcs)
+    _solve_linear(A.form, b.form, u, bcs, ident_zeros=A.ident)
 
 
 def project(expr, V=None, solver_type="lu", **kw):

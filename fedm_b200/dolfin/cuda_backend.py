@@ -53,7 +53,7 @@ class TorchStore:
 class CudaProblem:
     """One compiled residual form bound to a HotPath context."""
 
-    def __init__(self, backend, residual, u, bcs, quad_degree):
+    def __init__(self, backend, residual, u, bcs, quad_degree, ident_zeros=False):
         self.u, self.bcs = u, list(bcs)
         self.form = CompiledForm(residual, u, quad_degree)
         so = self.form.build()
@@ -62,7 +62,12 @@ class CudaProblem:
         self.hot = hot = hp.HotPath(backend.device_index)
         fd = self.form.facet_data
         if fd is not None:
-            hot.set_mesh(space.n_comp, tri.coords, tri.cells, fd.facets, fd.values)
+            # the fan tables carry a 4-bit marker per exterior facet with 0 = interior edge: unmarked exterior facets (still
+            # part of an un-indexed `ds`) travel as 15
+            vals = np.asarray(fd.values, dtype=np.int32)
+            if vals.size and vals.max() >= 15:
+                raise NotImplementedError("facet markers must be < 15 on the device path")
+            hot.set_mesh(space.n_comp, tri.coords, tri.cells, fd.facets, np.where(vals == 0, 15, vals).astype(np.int32))
         else:
             fv = tri.exterior_facets()
             hot.set_mesh(space.n_comp, tri.coords, tri.cells, fv, np.ones(fv.shape[0], dtype=np.int32))
@@ -76,6 +81,7 @@ class CudaProblem:
             hot.set_dirichlet(self.bc_comp, nodes, index)
             self.bc_nodes = nodes
         hot._ck(hot.lib.fedmx_plugin_load(hot.h, str(so).encode()))
+        hot._ck(hot.lib.fedmx_ident_zeros_set(hot.h, 1 if ident_zeros else 0))
         self._keep = []
         for k, (fn, comp) in enumerate(self.form.fields):
             t = fn.vector().store.t
@@ -93,7 +99,8 @@ class CudaProblem:
         """Two-stage AMG on the Dirichlet-constrained (potential) component: its diagonal block is the state-independent
         stiffness operator in every FEDM form; scalar problems without Dirichlet rows (projections, ToF) use Jacobi."""
         self.precond_ready = True
-        if self.bc_comp is None:
+        # multigrid needs an elliptic block: skip it when most rows are constrained (BoundaryGradient's anti-conditions)
+        if self.bc_comp is None or 2 * len(set(self.bc_nodes.tolist())) > self.hot.n_owned:
             return
         self.hot.jacobian(x, 1.0, 1.0)
         self.hot.setup_two_stage_preconditioner(self.bc_comp, self.bc_nodes)
@@ -133,5 +140,5 @@ class CudaBackend:
     def zeros(self, n, space=None):
         return TorchStore(n, self.device)
 
-    def compile(self, residual, u, bcs, quad_degree):
-        return CudaProblem(self, residual, u, bcs, quad_degree)
+    def compile(self, residual, u, bcs, quad_degree, ident_zeros=False):
+        return CudaProblem(self, residual, u, bcs, quad_degree, ident_zeros)

@@ -240,7 +240,12 @@ class CompiledForm:
             deg = quad_degree if quad_degree is not None else U.estimate_degree(g["expr"])
             self.groups.append((kind, sid, deg, U.test_function_split(g["expr"], self.n_eq)))
         self.source = self._generate()
-        self.key = hashlib.sha1(self.source.encode()).hexdigest()[:20]
+        # the cache key covers the library headers the plug-in is compiled against (AsmArgs / ModelParams layout)
+        h = hashlib.sha1(self.source.encode())
+        for name in ("row_kernel.cuh", "fedmx_internal.h", "dual.cuh"):
+            h.update((HERE / "csrc" / name).read_bytes())
+        h.update((HERE.parent / "include" / "fedmx.h").read_bytes())
+        self.key = h.hexdigest()[:20]
 
     # ---- symbol tables
     def field_slot(self, f):

@@ -5,8 +5,7 @@ compiler turns into CUDA row kernels; the solve is libfedmx's device Newton-Kryl
 Reference map: modify_approximation_vars :15-45, subdomains/marking :48-124, list helpers :127-171, Problem :174-202,
 Max/Min :205-216, Flux :219-237, weak forms :240-401, Boundary_flux :404-528, coefficient interpolation :531-750,
 semi_implicit_coefficients :753-774, Source_term :777-843, Energy_Source_term :845-912, controllers :915-951,
-adaptive_solver :958-1130.  (Normal_vector, Poisson_solver, BoundaryGradient -- never called by the examples -- are out of
-scope)
+adaptive_solver :958-1130, Normal_vector / Poisson_solver / BoundaryGradient :1133-1208.
 """
 import warnings
 
@@ -363,11 +362,48 @@ def adaptive_solver(nonlinear_solver, problem, t, dt, dt_old, u_new, u_old, var_
     return t
 
 
-def _out_of_scope(name):
-    def stub(*args, **kwargs):
-        raise NotImplementedError(f"fedm_b200.functions.{name} is outside the hot path (SURVEY.md section 8f)")
-    stub.__name__ = name
-    return stub
+def Normal_vector(mesh):
+    """Outward unit normal as a P1 vector field: L2 projection of the facet normal onto the boundary trace space; interior
+    dofs have no equation and are set to zero through ``ident_zeros`` (fedm/functions.py:1133-1151)."""
+    W = df.VectorFunctionSpace(mesh, "CG", 1)
+    u, v = df.TrialFunction(W), df.TestFunction(W)
+    facet_normal = df.FacetNormal(mesh)
+    A = df.assemble(df.inner(u, v) * df.ds, keep_diagonal=True)
+    b = df.assemble(df.inner(facet_normal, v) * df.ds)
+    A.ident_zeros()
+    n = df.Function(W)
+    df.solve(A, n.vector(), b, "mumps")
+    return n
 
 
-Normal_vector, Poisson_solver, BoundaryGradient = (_out_of_scope(n) for n in ("Normal_vector", "Poisson_solver", "BoundaryGradient"))
+def Poisson_solver(A, L, b, bcs, u, solver_type="mumps", preconditioner="hypre_amg"):
+    """Segregated Poisson step: re-assemble the right-hand side, apply the Dirichlet conditions and solve with the
+    pre-assembled matrix ``A`` (fedm/functions.py:1154-1161)."""
+    b = df.assemble(L, tensor=b)
+    for bc in bcs:
+        bc.apply(b)
+    extra = () if solver_type == "mumps" else (preconditioner,)
+    df.solve(A, u.vector(), b, solver_type, *extra)
+
+
+def BoundaryGradient(var, zeroDomain, source_term, ds_extract, epsilon=8.854187817e-12):
+    """Flux of ``-epsilon grad(var)`` through a boundary, recovered consistently from the weak Poisson residual instead of
+    differentiating the P1 field (D. Kamensky's boundary-flux trick, as adapted by fedm/functions.py:1164-1208): find
+    E on the boundary with  int eps E v ds = -(residual of the Poisson equation tested with v) + consistency term on
+    ds_extract[0];  all dofs inside ``zeroDomain`` (everything but the boundary of interest) are pinned to zero."""
+    V = var.ufl_function_space()
+    anti_bcs = [df.DirichletBC(V, df.Constant(0.0), zeroDomain())]
+    n = df.FacetNormal(V.mesh())
+    E, v = df.TrialFunction(V), df.TestFunction(V)
+    En = df.Function(V)
+    residual = epsilon * df.inner(df.grad(var), df.grad(v)) * df.dx - source_term * v * df.dx
+    F = residual - epsilon * df.inner(-df.grad(var), n) * v * ds_extract[0]
+    for _ in ds_extract[1:]:
+        F += epsilon * E * v * df.ds
+    A = df.assemble(df.lhs(F), keep_diagonal=True)
+    b = df.assemble(df.rhs(F))
+    for bc in anti_bcs:
+        bc.apply(A)
+        bc.apply(b)
+    df.solve(A, En.vector(), b, "gmres", "hypre_amg")
+    return En

@@ -69,6 +69,7 @@ SIGNATURES = {
     "fedmx_halo_set": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fedmx_halo_exchange": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "fedmx_allreduce_sum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "fedmx_ident_zeros_set": (C.c_int, [C.c_void_p, C.c_int]),
     "fedmx_pc_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "fedmx_peer_create": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_char_p]),
     "fedmx_peer_open": (C.c_int, [C.c_void_p, C.c_char_p]),

@@ -104,6 +104,8 @@ int fedmx_plugin_set_field(fedmx_ctx *ctx, int k, const double *d_ptr, int strid
 
 /* Per-node coefficient fields (P1 Functions: history terms, transport/rate coefficients...),
  * d_fields[n_vertices][n_fields], caller-owned. */
+/* dolfin's A.ident_zeros() (fedm/functions.py:1147): all-zero matrix rows get a unit diagonal (boundary-only forms). */
+int fedmx_ident_zeros_set(fedmx_ctx *ctx, int on);
 int fedmx_fields_bind(fedmx_ctx *ctx, int n_fields, const double *d_fields);
 
 /* ---- assembly (a1/a2: Problem.F / Problem.J, fedm/functions.py:188-202) --------------------------- */

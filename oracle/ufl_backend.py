@@ -180,8 +180,8 @@ def _fields(e, out):
 
 
 class CompiledProblem:
-    def __init__(self, residual, u, bcs, quad_degree):
-        self.u, self.bcs = u, bcs
+    def __init__(self, residual, u, bcs, quad_degree, ident_zeros=False):
+        self.u, self.bcs, self.ident_zeros = u, bcs, ident_zeros
         space = u.space
         tri = space.mesh().tri
         self.n_eq = space.n_comp
@@ -274,6 +274,11 @@ class CompiledProblem:
     def jacobian(self, x):
         _, J = self.element_tensors(x, jac=True)
         A = self.asm.scatter_matrix(J)
+        if self.ident_zeros:                       # dolfin's ident_zeros(): unit diagonal on all-zero rows
+            import scipy.sparse as sp
+            A = A.tocsr()
+            empty = np.asarray(abs(A).sum(axis=1)).ravel() == 0.0
+            A = (A + sp.diags(empty.astype(float))).tocsr()
         dofs, _ = self._bc()
         if dofs.size:
             A = apply_dirichlet_matrix(A, dofs)
@@ -299,5 +304,5 @@ class NumpyBackend:
     def zeros(self, n, space=None):
         return NumpyStore(n)
 
-    def compile(self, residual, u, bcs, quad_degree):
-        return CompiledProblem(residual, u, bcs, quad_degree)
+    def compile(self, residual, u, bcs, quad_degree, ident_zeros=False):
+        return CompiledProblem(residual, u, bcs, quad_degree, ident_zeros)

@@ -156,3 +156,21 @@ def test_glow_example_on_numpy_backend_matches_fenics_golden(tmp_path, golden_di
     for name in ("electrons", "Ar_plus", "Ar_star"):
         z = np.load(tmp_path / "number density" / name / f"{name}.npz")
         assert np.abs((z[f"{name}_1"][d2v] - g[name + "_1"]) / g[name + "_1"]).max() <= 1e-11
+
+
+def test_segregated_helpers_on_numpy_backend():
+    """Normal_vector / Poisson_solver / BoundaryGradient of the API mirror on the oracle's numpy backend: analytic checks
+    (unit normals on straight edges, nodally exact 1-D Poisson profile, consistent boundary flux)."""
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent))
+    from helpers_cases import check_helpers, run_helpers
+    from fedm_b200 import dolfin as df
+    from oracle.ufl_backend import NumpyBackend
+    df.set_backend(NumpyBackend())
+    df.parameters["form_compiler"]["quadrature_degree"] = None
+    try:
+        out = run_helpers(df, F)
+    finally:
+        df.set_backend(None)
+    check_helpers(out)

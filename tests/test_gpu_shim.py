@@ -73,3 +73,22 @@ def test_glow_discharge_script_on_gpu_matches_fenics_golden(cuda_shim, tmp_path,
         z = np.load(tmp_path / "number density" / name / f"{name}.npz")
         ref = g[name + "_1"]
         assert np.abs((z[f"{name}_1"][d2v] - ref) / ref).max() <= 1e-8, name
+
+
+def test_segregated_helpers_on_gpu_match_numpy_backend(cuda_shim):
+    """Normal_vector (vector space, boundary-only forms, ident_zeros), Poisson_solver and BoundaryGradient (trial functions in
+    facet integrals, Dirichlet conditions on interior dofs) of the API mirror: CUDA backend == numpy backend, plus the
+    analytic checks of tests/helpers_cases.py."""
+    sys.path.insert(0, str(ROOT / "tests"))
+    from helpers_cases import check_helpers, run_helpers
+    from fedm_b200 import functions as F
+    from oracle.ufl_backend import NumpyBackend
+    dolfin = cuda_shim
+    out = run_helpers(dolfin, F)
+    check_helpers(out)
+    dolfin.set_backend(NumpyBackend())
+    ref = run_helpers(dolfin, F)
+    dolfin.set_backend(None)
+    for key in ("normal", "phi", "flux"):
+        scale = np.abs(ref[key]).max()
+        assert np.abs(out[key] - ref[key]).max() <= 1e-9 * scale, key
