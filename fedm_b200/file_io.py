@@ -70,14 +70,19 @@ def read_and_decomment(file_name):
         return list(decomment(fh))
 
 
-def read_single_value(file_name, convert=lambda x: x):
+def no_convert(x):
+    """Identity, for readers that optionally convert what they read (fedm/file_io.py:123-129)."""
+    return x
+
+
+def read_single_value(file_name, convert=no_convert):
     with open(file_name, "r", encoding="utf8") as fh:
         for text in decomment(fh):
             return convert(text)
     raise RuntimeError(f"fedm.read_single_value: No value found in file '{file_name}'")
 
 
-def read_single_float(file_name, convert=None):
+def read_single_float(file_name, convert=no_convert):
     return read_single_value(file_name, convert=float)
 
 

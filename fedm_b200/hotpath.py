@@ -127,7 +127,7 @@ class HotPath:
         f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
         if local_mesh is None or local_mesh.world == 1:
             K = amg.symmetric_dirichlet(Kloc[:, :self.n_owned], bc[bc < self.n_owned])
-            levels, coarse_inv = amg.build_hierarchy(K, theta=theta)
+            levels, coarse_inv = amg.build_hierarchy(K, theta=theta, coarse_size=int(os.environ.get('FEDMX_AMG_COARSE', 600)))
             fine_ops = None
         else:
             import torch.distributed as dist
@@ -150,7 +150,7 @@ class HotPath:
             bcg[torch.from_numpy(l2g[bc[bc < self.n_owned]]).to(self.device)] = 1.0
             dist.all_reduce(bcg)
             Kg = amg.symmetric_dirichlet(Kg, np.nonzero(bcg.cpu().numpy() > 0)[0])
-            levels, coarse_inv = amg.build_hierarchy(Kg, theta=theta)
+            levels, coarse_inv = amg.build_hierarchy(Kg, theta=theta, coarse_size=int(os.environ.get('FEDMX_AMG_COARSE', 600)))
             owned_g = l2g[:self.n_owned]
             g2l = lm.global_to_local()
             A0 = levels[0]["A"][owned_g].tocsr()
