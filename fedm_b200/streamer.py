@@ -179,14 +179,56 @@ class StreamerCase:
         mk = lambda t: t.detach().cpu().pin_memory()
         return {"old": mk(self.x_new), "old1": mk(self.x_old), "new": mk(self.x_new)}
 
-    def step_host(self, hb):
-        """One step through host buffers: H2D of u_old and u_old1, solve, D2H of u_new (+ the scalar error)."""
-        self.x_old.copy_(hb["old"], non_blocking=True)
-        self.x_old1.copy_(hb["old1"], non_blocking=True)
+    def step_host(self, hb, chunks=8):
+        """One step through HOST buffers: u_old and u_old1 come from pinned host memory, u_new goes back to it.
+        The three PCIe transfers are pipelined on two copy streams (PCIe is full duplex):
+          * u_old1 of the NEXT step (= this step's hb['old'], already in host memory) is prefetched into a second device
+            buffer while this step computes;
+          * after the solve, u_new is written back in chunks and every chunk is re-uploaded as the next step's u_old as soon
+            as it has landed in host memory (device-to-host and host-to-device run concurrently).
+        The call returns when u_new is complete in hb; the trailing upload is awaited by the next call."""
+        main = torch.cuda.current_stream()
+        if not hasattr(self, "_h2d"):
+            self._h2d, self._d2h = torch.cuda.Stream(), torch.cuda.Stream()
+            self._old1_next = torch.empty_like(self.x_old1)
+            self._pending = None
+        if self._pending is None:                              # first call: plain uploads
+            self.x_old.copy_(hb["old"], non_blocking=True)
+            self.x_old1.copy_(hb["old1"], non_blocking=True)
+        else:                                                  # uploads issued by the previous call
+            ev_old, ev_old1 = self._pending
+            main.wait_event(ev_old)
+            main.wait_event(ev_old1)
+            self.x_old1, self._old1_next = self._old1_next, self.x_old1
         self.x_new.copy_(self.x_old)
+        start = torch.cuda.Event()
+        start.record(main)
+        # prefetch the next step's u_old1 (this step's u_old, host copy) while the solve runs
+        self._h2d.wait_event(start)
+        with torch.cuda.stream(self._h2d):
+            self._old1_next.copy_(hb["old"], non_blocking=True)
+            ev_old1 = torch.cuda.Event()
+            ev_old1.record(self._h2d)
         attempts = self._advance()
-        hb["new"].copy_(self.x_new, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        done = torch.cuda.Event()
+        done.record(main)
+        self._d2h.wait_event(done)
+        self._h2d.wait_event(done)                             # x_old is free once the solve has finished
+        n = self.x_new.numel()
+        step = (n + chunks - 1) // chunks
+        for lo in range(0, n, step):
+            hi = min(n, lo + step)
+            with torch.cuda.stream(self._d2h):
+                hb["new"][lo:hi].copy_(self.x_new[lo:hi], non_blocking=True)
+                landed = torch.cuda.Event()
+                landed.record(self._d2h)
+            self._h2d.wait_event(landed)
+            with torch.cuda.stream(self._h2d):
+                self.x_old[lo:hi].copy_(hb["new"][lo:hi], non_blocking=True)
+        ev_old = torch.cuda.Event()
+        ev_old.record(self._h2d)
+        self._d2h.synchronize()                                # the step's result is in host memory
+        self._pending = (ev_old, ev_old1)
         hb["old1"], hb["old"], hb["new"] = hb["old"], hb["new"], hb["old1"]
         return attempts
 

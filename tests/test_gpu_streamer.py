@@ -191,3 +191,18 @@ def test_interp_and_strided_copy():
     hot.strided_copy(src, 3, 1, dst, 1, 0, 10)
     assert np.array_equal(dst.cpu().numpy(), np.arange(30.0)[1::3])
     hot.close()
+
+
+def test_host_buffer_steps_equal_device_resident_steps():
+    """The end-to-end path (state in pinned host memory, transfers pipelined on two copy streams) must produce bit-identical
+    states and the same dt sequence as the device-resident path."""
+    a, b = StreamerCase(n=48), StreamerCase(n=48)
+    a.set_initial_state()
+    b.set_initial_state()
+    hb = b.make_host_buffers()
+    for _ in range(4):
+        a.step()
+        b.step_host(hb)
+        assert torch.equal(hb["old"], a.x_new.cpu())          # after the rotation hb['old'] holds the newest state
+    torch.cuda.synchronize()
+    assert torch.equal(a.x_new, b.x_new) and a.rows == b.rows
