@@ -10,6 +10,7 @@
 // (reference call site fedm/functions.py:1047); results do not depend on the preconditioner, only iteration counts.
 #include <algorithm>
 #include <stdlib.h>
+#include <string>
 
 #include <cooperative_groups.h>
 
@@ -164,26 +165,42 @@ __device__ __forceinline__ void for_rows(const ScalarSell &M, int64_t n, const d
     }
 }
 
-__global__ void __launch_bounds__(1024) coarse_vcycle_kernel(const CoarseLevelDev *L, int nl, int nu, const double *__restrict__ cinv) {
-    cg::cluster_group cluster = cg::this_cluster();
-    const int nt = int(cluster.num_blocks()) * blockDim.x;
-    const int tid = int(cluster.block_rank()) * blockDim.x + threadIdx.x;
-    // down: pre-smooth (zero initial guess), residual, restriction.  The current iterate always ends up in lv.x.
+// Body shared by the two fused variants: SYNC is a cluster barrier (one 8-CTA cluster, small levels) or a cooperative grid
+// barrier (whole GPU, mid levels).  Phases per level: residual | restriction (+ the zero-guess sweep of the next level) on the
+// way down, prolongation | Jacobi sweep on the way up; iterates ping-pong between x and x2 instead of being copied
+// (only the finest fused level, which the caller reads, is copied back into x).
+template <class Sync>
+__device__ __forceinline__ void coarse_vcycle_body(Sync sync, const int tid, const int nt, const CoarseLevelDev *L, int nl, int nu,
+                                                   const double *__restrict__ cinv) {
+    double *xa[12], *xb[12];                                  // current iterate / scratch per level
+    for (int l = 0; l < nl; ++l) { xa[l] = L[l].x; xb[l] = L[l].x2; }
+    {   // zero-guess sweep of the finest fused level (its right-hand side was produced by the preceding kernel)
+        const CoarseLevelDev &lv = L[0];
+        if (nl > 1) {
+            for (int64_t i = tid; i < lv.n; i += nt) xa[0][i] = lv.omega * lv.dinv[i] * lv.b[i];
+            sync();
+        }
+    }
     for (int l = 0; l < nl - 1; ++l) {
         const CoarseLevelDev &lv = L[l];
-        for (int64_t i = tid; i < lv.n; i += nt) lv.x[i] = lv.omega * lv.dinv[i] * lv.b[i];
-        cluster.sync();
         for (int sweep = 1; sweep < nu; ++sweep) {
-            for_rows(lv.A, lv.n, lv.x, tid, nt, 8, [&](int64_t i, double t) { lv.x2[i] = lv.x[i] + lv.omega * lv.dinv[i] * (lv.b[i] - t); });
-            cluster.sync();
-            for (int64_t i = tid; i < lv.n; i += nt) lv.x[i] = lv.x2[i];
-            cluster.sync();
+            const double *xc = xa[l];
+            double *xn = xb[l];
+            for_rows(lv.A, lv.n, xc, tid, nt, 8, [&](int64_t i, double t) { xn[i] = xc[i] + lv.omega * lv.dinv[i] * (lv.b[i] - t); });
+            sync();
+            xb[l] = xa[l];
+            xa[l] = xn;
         }
-        for_rows(lv.A, lv.n, lv.x, tid, nt, 8, [&](int64_t i, double t) { lv.r[i] = lv.b[i] - t; });
-        cluster.sync();
-        double *bc = L[l + 1].b;
-        for_rows(lv.R, lv.n_coarse, lv.r, tid, nt, 32, [&](int64_t i, double t) { bc[i] = t; });
-        cluster.sync();
+        for_rows(lv.A, lv.n, xa[l], tid, nt, 8, [&](int64_t i, double t) { lv.r[i] = lv.b[i] - t; });
+        sync();
+        const CoarseLevelDev &lc = L[l + 1];
+        const bool sweep_next = l + 1 < nl - 1;
+        double *xnext = xa[l + 1];
+        for_rows(lv.R, lv.n_coarse, lv.r, tid, nt, 32, [&](int64_t i, double t) {
+            lc.b[i] = t;
+            if (sweep_next) xnext[i] = lc.omega * lc.dinv[i] * t;
+        });
+        sync();
     }
     {   // coarsest level: dense inverse, one warp per row
         const CoarseLevelDev &lc = L[nl - 1];
@@ -194,23 +211,66 @@ __global__ void __launch_bounds__(1024) coarse_vcycle_kernel(const CoarseLevelDe
             for (int j = lane; j < n; j += 32) acc = fma(cinv[int64_t(row) * n + j], lc.b[j], acc);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (lane == 0) lc.x[row] = acc;
+            if (lane == 0) xa[nl - 1][row] = acc;
         }
-        cluster.sync();
+        sync();
     }
-    // up: prolongation + correction, post-smooth
     for (int l = nl - 2; l >= 0; --l) {
         const CoarseLevelDev &lv = L[l];
-        const double *xc = L[l + 1].x;
-        for_rows(lv.P, lv.n, xc, tid, nt, 4, [&](int64_t i, double t) { lv.x[i] += t; });
-        cluster.sync();
+        double *xc = xa[l];
+        for_rows(lv.P, lv.n, xa[l + 1], tid, nt, 4, [&](int64_t i, double t) { xc[i] += t; });
+        sync();
         for (int sweep = 0; sweep < nu; ++sweep) {
-            for_rows(lv.A, lv.n, lv.x, tid, nt, 8, [&](int64_t i, double t) { lv.x2[i] = lv.x[i] + lv.omega * lv.dinv[i] * (lv.b[i] - t); });
-            cluster.sync();
-            for (int64_t i = tid; i < lv.n; i += nt) lv.x[i] = lv.x2[i];
-            cluster.sync();
+            const double *xo = xa[l];
+            double *xn = xb[l];
+            for_rows(lv.A, lv.n, xo, tid, nt, 8, [&](int64_t i, double t) { xn[i] = xo[i] + lv.omega * lv.dinv[i] * (lv.b[i] - t); });
+            sync();
+            xb[l] = xa[l];
+            xa[l] = xn;
         }
     }
+    if (xa[0] != L[0].x) {                                     // the caller reads the result from L[0].x
+        const double *src = xa[0];
+        double *dst = L[0].x;
+        for (int64_t i = tid; i < L[0].n; i += nt) dst[i] = src[i];
+    }
+}
+
+__global__ void __launch_bounds__(1024) coarse_vcycle_kernel(const CoarseLevelDev *L, int nl, int nu, const double *__restrict__ cinv) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int nt = int(cluster.num_blocks()) * blockDim.x;
+    const int tid = int(cluster.block_rank()) * blockDim.x + threadIdx.x;
+    coarse_vcycle_body([&]() { cluster.sync(); }, tid, nt, L, nl, nu, cinv);
+}
+
+// Whole-GPU variant (cooperative launch, all CTAs co-resident): the mid levels (62 k - 555 k rows) need every SM's load/store
+// bandwidth, and a grid barrier (~1.5 us) is still cheaper than a kernel boundary plus launch (~5-8 us for these sizes).
+// Grid barrier: one arrive counter + a generation word (release/acquire at gpu scope; the acquire also drops stale L1 lines).
+__device__ __forceinline__ void grid_barrier(unsigned int *state) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int gen;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(state + 1) : "memory");
+        __threadfence();
+        if (atomicAdd(state, 1u) == gridDim.x - 1) {
+            state[0] = 0;
+            __threadfence();
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(state + 1), "r"(gen + 1) : "memory");
+        } else {
+            unsigned int now;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(now) : "l"(state + 1) : "memory");
+            } while (now == gen);
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(512) coarse_vcycle_grid_kernel(const CoarseLevelDev *L, int nl, int nu, const double *__restrict__ cinv,
+                                                                 unsigned int *barrier_state) {
+    const int nt = int(gridDim.x) * blockDim.x;
+    const int tid = int(blockIdx.x) * blockDim.x + threadIdx.x;
+    coarse_vcycle_body([&]() { grid_barrier(barrier_state); }, tid, nt, L, nl, nu, cinv);
 }
 
 __global__ void comp_scatter_kernel(const double *__restrict__ e, double *__restrict__ z, int neq, int comp, int64_t n) {
@@ -267,11 +327,34 @@ void launch_ssell(fedmx_ctx *ctx, const ScalarSell &A, const double *x, const do
 static const int64_t kFuseRows = getenv("FEDMX_FUSE_ROWS") ? atoll(getenv("FEDMX_FUSE_ROWS")) : 3000;  // one cluster of 8 CTAs; measured on B200: 3000, 8000 and 80000 rows give 26.8 / 26.9 / 29.9 ms per step (8 SMs cannot feed larger levels)
 constexpr int kClusterSize = 8;
 
+// FEDMX_MG_FUSE=cluster (default): only the levels of up to kFuseRows rows are fused (one cluster), the others are separate
+// launches.  FEDMX_MG_FUSE=grid: levels of up to kGridFuseRows rows run inside ONE cooperative whole-GPU kernel.  Measured on
+// B200 at 10 M DOF: the grid variant needs 182-195 us for the levels below the finest one against 149 us (mid 121 + cluster 27)
+// with separate launches -- a persistent grid has 4x fewer threads than rows on the 555 k-row level, so its gathers run with a
+// quarter of the memory-level parallelism; the barrier flavour (cooperative_groups or the hand-written one) makes no difference.
+static const bool kGridFuse = getenv("FEDMX_MG_FUSE") && std::string(getenv("FEDMX_MG_FUSE")) == "grid";
+static const int64_t kGridFuseRows = getenv("FEDMX_GRID_FUSE_ROWS") ? atoll(getenv("FEDMX_GRID_FUSE_ROWS")) : 1000000;
+
 static int setup_coarse_fusion(fedmx_ctx *ctx) {
     auto &L = ctx->amg_levels;
     const int nl = int(L.size());
     int first = nl - 1;
-    while (first > 0 && L[first - 1].n <= kFuseRows) --first;
+    int coop = 0;
+    FEDMX_CHECK_CUDA(ctx, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
+    ctx->coarse_grid_blocks = 0;
+    if (kGridFuse && coop && nl <= 12) {
+        int per_sm = 0, sms = 0;
+        FEDMX_CHECK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, coarse_vcycle_grid_kernel, 512, 0));
+        FEDMX_CHECK_CUDA(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+        ctx->coarse_grid_blocks = std::min(per_sm, 2) * sms;
+        if (!ctx->d_grid_barrier) {
+            int rc = fedmx_dev_alloc(ctx, &ctx->d_grid_barrier, 2);
+            if (rc) return rc;
+            FEDMX_CHECK_CUDA(ctx, cudaMemset(ctx->d_grid_barrier, 0, 2 * sizeof(unsigned int)));
+        }
+    }
+    const int64_t limit = ctx->coarse_grid_blocks > 0 ? kGridFuseRows : kFuseRows;
+    while (first > 0 && L[first - 1].n <= limit) --first;
     if (ctx->n_ranks > 1 && first == 0) first = 1;          // the finest level of a partitioned run needs halo exchanges
     if (first > nl - 1) first = nl - 1;
     std::vector<CoarseLevelDev> h(nl - first);
@@ -325,7 +408,17 @@ int fedmx_amg_vcycle(fedmx_ctx *ctx, double *z_out, int z_stride, int z_off) {
         // distributed fine level: R holds only this rank's fine columns; the coarse right-hand side is the sum over ranks
         if (dist && (rc = fedmx_global_sum(ctx, L[l + 1].b, int(L[l + 1].n)))) return rc;
     }
-    {
+    if (ctx->coarse_grid_blocks > 0) {
+        ProfScope cprof(ctx, FEDMX_PROF_MG_COARSE);
+        const CoarseLevelDev *levels = (const CoarseLevelDev *)ctx->d_coarse_levels;
+        int count = ctx->coarse_count, sweeps = nu;
+        const double *cinv = ctx->amg_coarse_inv;
+        unsigned int *bstate = ctx->d_grid_barrier;
+        void *args[] = {(void *)&levels, (void *)&count, (void *)&sweeps, (void *)&cinv, (void *)&bstate};
+        FEDMX_CHECK_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)coarse_vcycle_grid_kernel, dim3(ctx->coarse_grid_blocks),
+                                                          dim3(512), args, 0, ctx->stream));
+        ctx->launches++;
+    } else {
         ProfScope cprof(ctx, FEDMX_PROF_MG_COARSE);
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(kClusterSize);

@@ -150,6 +150,8 @@ struct fedmx_ctx {
     double *d_tmp = nullptr;
     void *d_coarse_levels = nullptr;   // device array of fused coarse-level descriptors
     int coarse_first = -1, coarse_count = 0;
+    unsigned int *d_grid_barrier = nullptr;
+    int coarse_grid_blocks = 0;        // > 0: the coarse levels run in one cooperative whole-GPU kernel of this many CTAs
     // profiling (CUDA events around kernel classes)
     int prof_on = 0;                         // 0 off, 1 kernel classes, 2 + nested break-down (more event records)
     std::vector<cudaEvent_t> prof_ev[FEDMX_PROF_KINDS];     // start/stop pairs per kind
