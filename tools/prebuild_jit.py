@@ -1,0 +1,53 @@
+"""Pre-compile the form-compiler plug-ins that the examples and the GPU tests use (CPU container: nvcc cross-compiles sm_100a).
+
+The scripts are executed at tiny size on the oracle's numpy backend (test infrastructure: here it only drives the scripts so
+that every form they hand to the backend is seen); each form is lowered by fedm_b200.formcompiler and built into
+fedm_b200/jit_cache/, where the GPU box finds it by hash (source + library headers) instead of running nvcc at test time."""
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path[:0] = [str(ROOT), str(ROOT / "compat"), str(ROOT / "examples"), str(ROOT / "tests")]
+
+
+def main():
+    import dolfin
+    from fedm_b200.formcompiler import CompiledForm
+    from oracle.ufl_backend import NumpyBackend
+
+    built = []
+
+    class Recorder(NumpyBackend):
+        def compile(self, residual, u, bcs, quad_degree, ident_zeros=False):
+            t0 = time.time()
+            so = CompiledForm(residual, u, quad_degree).build()
+            built.append((so.name, time.time() - t0))
+            return super().compile(residual, u, bcs, quad_degree, ident_zeros=ident_zeros)
+
+    dolfin.set_backend(Recorder())
+    golden = ROOT / "tests" / "golden"
+    try:
+        with tempfile.TemporaryDirectory() as tmp:
+            tmp = Path(tmp)
+            import glow_discharge
+            import streamer_discharge
+            import time_of_flight
+            streamer_discharge.main(n=6, input_dir=golden / "streamer_discharge_input", output_dir=tmp / "s", linear_solver="mumps", max_steps=1)
+            dolfin.parameters["form_compiler"]["quadrature_degree"] = None
+            time_of_flight.main(output_dir=tmp / "t", nx=4, ny=4, T_final=2.5e-9 + 2e-12)
+            glow_discharge.main(input_dir=golden / "glow_discharge_input", output_dir=tmp / "g", nx=4, max_steps=1)
+            dolfin.parameters["form_compiler"]["quadrature_degree"] = None
+            from fedm_b200 import functions as F
+            from helpers_cases import run_helpers
+            run_helpers(dolfin, F, n=4)
+    finally:
+        dolfin.set_backend(None)
+        dolfin.parameters["form_compiler"]["quadrature_degree"] = None
+    names = sorted({b[0] for b in built})
+    print(f"prebuilt {len(names)} form plug-ins in {sum(b[1] for b in built):.1f} s:", ", ".join(names))
+
+
+if __name__ == "__main__":
+    main()
