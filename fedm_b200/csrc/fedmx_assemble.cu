@@ -30,7 +30,7 @@ namespace {
 // fields: [0]=hist_i [1]=hist_e  (BDF2 history, fedmx_bdf2_history)
 // =====================================================================================================
 struct StreamerModel {
-    static constexpr int MINB = 2, MINB_RES = 4;
+    static constexpr int MINB = 13, MINB_RES = 4;       // Jacobian: 3 CTAs/SM with the accumulator blocks in shared memory
     static constexpr unsigned ZERO_MASK = 1u << 3;      // d R_e / d U_i == 0: the electron equation does not see the ions
     static constexpr int NEQ = 3;
     static constexpr int NF = 2;
@@ -389,9 +389,11 @@ int launch_assembly(fedmx_ctx *ctx, const double *d_x, double *d_b, bool jac) {
     A.res = d_b;
     A.mp = ctx->mp;
     ProfScope prof(ctx, jac ? FEDMX_PROF_ASM_JAC : FEDMX_PROF_ASM_RES);
-    // resident CTAs per SM the kernel is compiled for (register cap 65536/(128*MINB)); FEDMX_ASM_MINB overrides for tuning.
-    // measured on B200 at 10 M DOF (tools/bench_assembly.py): Jacobian 1.07/1.13/1.51 ms and residual 0.76/0.57/0.56 ms
-    // for 2/3/4 resident CTAs per SM
+    // resident CTAs per SM the kernel is compiled for (register cap 65536/(128*MINB)); 1x = the same with the diag/carry
+    // accumulators in shared memory (row_kernel.cuh).  FEDMX_ASM_MINB overrides for tuning.  Measured on B200 at 10 M DOF
+    // (tools/bench_assembly.py, incl. nodal exp + block-Jacobi update): Jacobian 1.10 / 1.14 ms for 2 / 3 CTAs with register
+    // accumulators (3 CTAs: 464 B of spills), 0.97 / 1.30 ms for 3 / 4 CTAs with shared-memory accumulators (136 B / 408 B of
+    // spills); residual 0.77 / 0.58 / 0.56 ms for 2 / 3 / 4 CTAs.  All variants produce bit-identical matrices.
     static const int env_minb = getenv("FEDMX_ASM_MINB") ? atoi(getenv("FEDMX_ASM_MINB")) : 0;
     const int minb = env_minb ? env_minb : (jac ? Model::MINB : Model::MINB_RES);
     launch_rows<Model>(A, jac, minb, ctx->stream);

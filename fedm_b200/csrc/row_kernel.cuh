@@ -100,10 +100,14 @@ __device__ __forceinline__ void zero_row(double *blk, int comp) {
             if (k == comp) blk[k * NEQ + l] = 0.0;
 }
 
-template <class Model, bool JAC, int MINB>
+// SACC: the two accumulator blocks (diag, carry: 2 n_eq^2 doubles per thread) live in shared memory instead of registers
+// ([entry][thread]: conflict-free), which frees 4 n_eq^2 registers for a third resident CTA per SM.
+template <class Model, bool JAC, int MINB, bool SACC = false>
 __global__ void __launch_bounds__(128, MINB) assemble_rows_kernel(AsmArgs A) {
     constexpr int NEQ = Model::NEQ, NF = Model::NF, NC = Model::NC, NB = NEQ * NEQ;
     constexpr unsigned ZMASK = Model::ZERO_MASK;
+    __shared__ double sacc[(SACC && JAC) ? 2 * NB : 1][(SACC && JAC) ? 128 : 1];
+    const int tid = threadIdx.x;
     const int64_t row = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     const int64_t s = row / FEDMX_SLICE;
     const int lane = int(row % FEDMX_SLICE);
@@ -121,9 +125,14 @@ __global__ void __launch_bounds__(128, MINB) assemble_rows_kernel(AsmArgs A) {
     Vtx<NEQ, NF, NC> va;
     if (active) load_vertex<NEQ, NF, NC>(A, int32_t(row), va);
 
-    double diag[NB], carry[NB], R[NEQ];
+    double diag[SACC ? 1 : NB], carry[SACC ? 1 : NB], R[NEQ];
+    if constexpr (SACC && JAC) {
 #pragma unroll
-    for (int e = 0; e < NB; ++e) { diag[e] = 0.0; carry[e] = 0.0; }
+        for (int e = 0; e < 2 * NB; ++e) sacc[e][tid] = 0.0;
+    } else {
+#pragma unroll
+        for (int e = 0; e < NB; ++e) { diag[e] = 0.0; carry[e] = 0.0; }
+    }
 #pragma unroll
     for (int k = 0; k < NEQ; ++k) R[k] = 0.0;
 
@@ -151,7 +160,26 @@ __global__ void __launch_bounds__(128, MINB) assemble_rows_kernel(AsmArgs A) {
         Model::template row<JAC>(A.mp, va, p, n, PACK_MK_N(pack), PACK_MK_P(pack), o);
 #pragma unroll
         for (int k = 0; k < NEQ; ++k) R[k] += o.R[k];
-        if (JAC) {
+        if constexpr (JAC && SACC) {
+            double blk[NB];
+#pragma unroll
+            for (int q = 0; q < NB; ++q) sacc[q][tid] += o.J[0][q];
+            const bool first = PACK_FIRST(pack);
+#pragma unroll
+            for (int q = 0; q < NB; ++q) blk[q] = (first ? 0.0 : sacc[NB + q][tid]) + o.J[1][q];
+            if (bc) zero_row<NEQ>(blk, bc_comp);
+            store_block<NEQ, ZMASK>(A, gbase, PACK_SLOT_P(pack), lane, blk);   // block (i, vp) complete: write it
+            if (PACK_LAST(pack)) {
+#pragma unroll
+                for (int q = 0; q < NB; ++q) blk[q] = o.J[2][q];
+                if (bc) zero_row<NEQ>(blk, bc_comp);
+                if (PACK_CLOSED(pack)) add_block<NEQ, ZMASK>(A, gbase, PACK_SLOT_N(pack), lane, blk);
+                else store_block<NEQ, ZMASK>(A, gbase, PACK_SLOT_N(pack), lane, blk);
+            } else {
+#pragma unroll
+                for (int q = 0; q < NB; ++q) sacc[NB + q][tid] = o.J[2][q];
+            }
+        } else if constexpr (JAC) {
 #pragma unroll
             for (int q = 0; q < NB; ++q) diag[q] += o.J[0][q];
             if (PACK_FIRST(pack)) {
@@ -179,16 +207,24 @@ __global__ void __launch_bounds__(128, MINB) assemble_rows_kernel(AsmArgs A) {
         pack0 = pack1;
     }
     if (!active) return;
+    double dblk[NB];
+    if constexpr (JAC) {
+#pragma unroll
+        for (int q = 0; q < NB; ++q) {
+            if constexpr (SACC) dblk[q] = sacc[q][tid];
+            else dblk[q] = diag[q];
+        }
+    }
     if (bc) {
         const double g = A.mp.bc_values[bc - 1];
 #pragma unroll
         for (int k = 0; k < NEQ; ++k)
             if (k == bc_comp) R[k] = va.u[k] - g;
         if (JAC) {
-            zero_row<NEQ>(diag, bc_comp);
+            zero_row<NEQ>(dblk, bc_comp);
 #pragma unroll
             for (int k = 0; k < NEQ; ++k)
-                if (k == bc_comp) diag[k * NEQ + k] = 1.0;
+                if (k == bc_comp) dblk[k * NEQ + k] = 1.0;
         }
     }
     if (JAC && A.mp.ident_zeros) {
@@ -198,13 +234,13 @@ __global__ void __launch_bounds__(128, MINB) assemble_rows_kernel(AsmArgs A) {
         for (int k = 0; k < NEQ; ++k) {
             bool zero = true;
 #pragma unroll
-            for (int l = 0; l < NEQ; ++l) zero = zero && diag[k * NEQ + l] == 0.0;
+            for (int l = 0; l < NEQ; ++l) zero = zero && dblk[k * NEQ + l] == 0.0;
 #pragma unroll
             for (int l = 0; l < NEQ; ++l)
-                if (l == k && zero) diag[k * NEQ + l] = 1.0;
+                if (l == k && zero) dblk[k * NEQ + l] = 1.0;
         }
     }
-    if (JAC) store_block<NEQ, ZMASK>(A, gbase, diag_slot, lane, diag);
+    if (JAC) store_block<NEQ, ZMASK>(A, gbase, diag_slot, lane, dblk);
     if (A.res) {
 #pragma unroll
         for (int k = 0; k < NEQ; ++k) A.res[int64_t(NEQ) * row + k] = R[k];
@@ -219,6 +255,11 @@ inline void launch_rows(const AsmArgs &A, bool jac, int minb, cudaStream_t strea
     const int64_t rows = A.S.n_slices * FEDMX_SLICE;
     const unsigned blocks = unsigned((rows + threads - 1) / threads);
     if (jac) {
+        if constexpr (2 * Model::NEQ * Model::NEQ * 128 * 8 <= 48 * 1024) {      // accumulators in (static) shared memory
+            if (minb == 13) { assemble_rows_kernel<Model, true, 3, true><<<blocks, threads, 0, stream>>>(A); return; }
+            if (minb == 14) { assemble_rows_kernel<Model, true, 4, true><<<blocks, threads, 0, stream>>>(A); return; }
+        }
+        if (minb > 10) minb -= 10;
         if (minb >= 4) assemble_rows_kernel<Model, true, 4><<<blocks, threads, 0, stream>>>(A);
         else if (minb == 3) assemble_rows_kernel<Model, true, 3><<<blocks, threads, 0, stream>>>(A);
         else assemble_rows_kernel<Model, true, 2><<<blocks, threads, 0, stream>>>(A);

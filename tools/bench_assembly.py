@@ -25,3 +25,12 @@ tj = timeit(lambda: hot.lib.fedmx_assemble_jacobian(hot.h, x.data_ptr(), 5e-12, 
 tr = timeit(lambda: hot.residual(x, 5e-12, 1e30, out=b))
 ts = timeit(lambda: hot.spmv(x, b))
 print(f"n={n} dof={dof} MINB={os.environ.get('FEDMX_ASM_MINB','default')}: jacobian {tj:.3f} ms ({dof/tj/1e6:.2f} GDOF/s, {2.1328e9*(dof/10002828)/tj/1e6:.0f} GB/s)  residual {tr:.3f} ms  spmv {ts:.3f} ms")
+# bit-level check of the kernel variant selected by FEDMX_ASM_MINB on a small mesh: print a checksum of the assembled matrix
+small = StreamerCase(n=96, precond="bjacobi")
+ui, ue = small.initial_log_densities()
+xs = torch.from_numpy(np.stack([ui, ue, 18750.0 * small.mesh.coords[:, 1] / 0.0125 + 50 * np.sin(small.mesh.coords[:, 0] * 2000)], axis=1).ravel()).to(small.device)
+small.hot.bdf2_history(2, xs, xs, 5e-12, 1e30)
+small.hot.jacobian(xs, 5e-12, 1e30)
+vals = small.hot.matrix_bsr()[2]
+import hashlib
+print("matrix sha1", hashlib.sha1(vals.tobytes()).hexdigest()[:16], "sum", float(vals.sum()))
