@@ -23,7 +23,7 @@ int fedmx_global_sum(fedmx_ctx *ctx, double *d_buf, int n);
 
 namespace {
 
-enum { MODE_MULT = 0, MODE_RESID = 1, MODE_JACOBI = 2, MODE_ADD = 3, MODE_JACOBI_OUT = 4 };
+enum { MODE_MULT = 0, MODE_RESID = 1, MODE_JACOBI = 2, MODE_ADD = 3, MODE_JACOBI_OUT = 4, MODE_FIRST_RESID = 5 };
 
 // MODE_JACOBI_OUT: the last sweep of the cycle writes its result straight into component `yo` of the node-interleaved
 // preconditioned vector (y[row*ys + yo]) instead of the level's iterate.
@@ -38,6 +38,19 @@ __global__ void __launch_bounds__(128) ssell_kernel(ScalarSell A, const double *
     const int width = A.slice_width[s];
     const int64_t base = A.slice_ptr[s] + lane;
     double t = 0.0;
+    if (MODE == MODE_FIRST_RESID) {
+        // zero-guess sweep fused with the residual: x = omega Dinv b is formed on the fly at the neighbours (b and dinv are
+        // gathered instead of x), x itself is written for the later prolongation:  y = b - A (omega Dinv b), ys/yo unused
+        for (int k = 0; k < width; ++k) {
+            const int64_t e = base + int64_t(k) * FEDMX_SLICE;
+            const int32_t c = A.col[e];
+            t = fma(double(A.val[e]), omega * __ldg(dinv + c) * __ldg(b + c), t);
+        }
+        if (row >= A.n_rows) return;
+        const_cast<double *>(x)[row] = omega * dinv[row] * b[row];
+        y[row] = b[row] - t;
+        return;
+    }
     for (int k = 0; k < width; ++k) {
         const int64_t e = base + int64_t(k) * FEDMX_SLICE;
         t = fma(double(A.val[e]), __ldg(x + A.col[e]), t);
@@ -389,8 +402,13 @@ int fedmx_amg_vcycle(fedmx_ctx *ctx, double *z_out, int z_stride, int z_off) {
         ProfScope lprof(ctx, l == 0 ? FEDMX_PROF_MG_FINE : FEDMX_PROF_MG_MID);
         AmgLevel &lv = L[l];
         const unsigned vb = unsigned((lv.n + 255) / 256);
-        first_sweep_kernel<<<vb, 256, 0, ctx->stream>>>(lv.b, lv.dinv, lv.omega, lv.x, lv.n);
-        ctx->launches++;
+        const bool fuse_first = nu == 1 && !(l == 0 && ctx->n_ranks > 1);   // distributed level: ghosts of x come by halo exchange
+        if (fuse_first) {
+            launch_ssell<MODE_FIRST_RESID>(ctx, lv.A, lv.x, lv.b, lv.dinv, lv.omega, lv.r);
+        } else {
+            first_sweep_kernel<<<vb, 256, 0, ctx->stream>>>(lv.b, lv.dinv, lv.omega, lv.x, lv.n);
+            ctx->launches++;
+        }
         for (int sweep = 1; sweep < nu; ++sweep) {
             if (l == 0 && ctx->n_ranks > 1 && (rc = fedmx_halo_exchange_internal(ctx, lv.x, 1))) return rc;
             launch_ssell<MODE_JACOBI>(ctx, lv.A, lv.x, lv.b, lv.dinv, lv.omega, lv.x2);
@@ -398,7 +416,7 @@ int fedmx_amg_vcycle(fedmx_ctx *ctx, double *z_out, int z_stride, int z_off) {
         }
         const bool dist = (l == 0 && ctx->n_ranks > 1);
         if (dist && (rc = fedmx_halo_exchange_internal(ctx, lv.x, 1))) return rc;      // ghosts of x for A x
-        launch_ssell<MODE_RESID>(ctx, lv.A, lv.x, lv.b, nullptr, 0.0, lv.r);
+        if (!fuse_first) launch_ssell<MODE_RESID>(ctx, lv.A, lv.x, lv.b, nullptr, 0.0, lv.r);
         {
             constexpr int LPR = 4;
             const unsigned rb = unsigned((lv.R.n_rows * LPR + 127) / 128);
