@@ -1,0 +1,107 @@
+"""CPU tests of the script-facing tool chain that replaces FFC/UFL/dijitso for the hot path (no GPU needed):
+the C++ Expression-string parser, UFL-lite (degree estimation as UFL's SumDegreeEstimator, lhs/rhs, action, test-function
+split) and the form compiler's code generation + nvcc cross-compilation of a plug-in."""
+import ctypes
+import math
+
+import numpy as np
+import pytest
+
+from fedm_b200 import cexpr
+from fedm_b200 import dolfin as df
+from fedm_b200 import functions as F
+from fedm_b200 import ufl as U
+
+
+def test_expression_strings_of_the_reference_scripts_evaluate_like_numpy():
+    x0, x1 = np.linspace(0.0, 2.5e-4, 7), np.linspace(0.0, 5e-4, 7)
+    p = dict(D=0.12, w=1.7e5, alpha=5009.51, t=2.5e-9, pi=math.pi)
+    # fedm_tof.py:116 (analytic swarm), fedm_gd.py:272 (powered electrode), fedm_streamer.py:177 (seed)
+    cases = {
+        "std::log(exp(-(pow(x[1]-w*t, 2)+pow(x[0], 2))/(4.0*D*t)+alpha*w*t)/pow(4*D*t*pi,1.5))":
+            np.log(np.exp(-((x1 - p["w"] * p["t"]) ** 2 + x0 ** 2) / (4.0 * p["D"] * p["t"]) + p["alpha"] * p["w"] * p["t"]) / (4 * p["D"] * p["t"] * math.pi) ** 1.5),
+        "U0*(1-exp(-t/1e-9))": -250.0 * (1 - math.exp(-2.5)) * np.ones(7),
+        "std::log(1e13 + 5e18*exp(-(pow(x[0], 2) + pow(x[1]-1e-2, 2))/pow(0.4e-3, 2)))":
+            np.log(1e13 + 5e18 * np.exp(-(x0 ** 2 + (x1 - 1e-2) ** 2) / 0.4e-3 ** 2)),
+        "-x[0] + 2.0*-3.0 + DOLFIN_EPS": -x0 - 6.0 + 3.0e-16,
+    }
+    for text, ref in cases.items():
+        got = cexpr.evaluate(cexpr.parse(text), (x0, x1), dict(p, U0=-250.0))
+        assert np.allclose(np.broadcast_to(got, ref.shape), ref, rtol=1e-15, atol=0.0), text
+    with pytest.raises(SyntaxError):
+        cexpr.parse("pow(x[0], )")
+
+
+@pytest.fixture(autouse=True)
+def numpy_storage():
+    """Functions need a vector store: on the CPU the oracle's numpy backend provides it (the product default, CUDA, refuses to
+    start without a GPU)."""
+    from oracle.ufl_backend import NumpyBackend
+    df.set_backend(NumpyBackend())
+    df.parameters["form_compiler"]["quadrature_degree"] = None
+    yield
+    df.set_backend(None)
+    df.parameters["form_compiler"]["quadrature_degree"] = None
+
+
+def _tof_form(mesh):
+    V = df.FunctionSpace(mesh, "P", 1)
+    W = df.VectorFunctionSpace(mesh, "P", 1)
+    u, v = df.TrialFunction(V), df.TestFunction(V)
+    u_old, u_old1, u_new = df.Function(V), df.Function(V), df.Function(V)
+    dt = df.Expression("time_step", time_step=1e-12, degree=0)
+    dt_old = df.Expression("time_step", time_step=1e30, degree=0)
+    r = df.Expression("x[0]", degree=1)
+    w = df.interpolate(df.Constant(("0", 1.7e5)), W)
+    D = df.interpolate(df.Constant(0.12), V)
+    f = df.Expression("exp(-(pow(x[1]-w*t, 2)+pow(x[0], 2))/(4.0*D*t))", D=0.12, w=1.7e5, t=2.5e-9, degree=2)
+    Gamma = -df.grad(D * df.exp(u)) + w * df.exp(u)
+    form = F.weak_form_balance_equation_log_representation("drift-diffusion-reaction", dt, dt_old, df.dx, u, u_old, u_old1, v, f, Gamma, r)
+    return df.action(form, u_new), u_new
+
+
+def test_degree_estimation_matches_ufl_on_the_time_of_flight_form():
+    """FFC integrates the ToF form with the degree UFL estimates (no global quadrature degree is set): 8, i.e. the 25-point
+    collapsed Gauss-Jacobi rule that the golden VTU pins."""
+    df.parameters["form_compiler"]["quadrature_degree"] = None
+    form, _ = _tof_form(df.RectangleMesh(df.Point(0, 0), df.Point(1, 1), 2, 2))
+    total = U.Const(0.0)
+    for it in form.integrals:
+        total = total + it.integrand
+    assert U.estimate_degree(total) == 8
+
+
+def test_lhs_rhs_and_action_on_the_poisson_form():
+    mesh = df.RectangleMesh(df.Point(0, 0), df.Point(1, 1), 2, 2)
+    V = df.FunctionSpace(mesh, "P", 1)
+    u, v = df.TrialFunction(V), df.TestFunction(V)
+    form = F.weak_form_Poisson_equation(df.dx, u, v, df.Constant(3.0))
+    a, L = df.lhs(form), df.rhs(form)
+    assert all(U._has_trial(i.integrand) for i in a.integrals if not isinstance(i.integrand, U.Const))
+    assert not any(U._has_trial(i.integrand) for i in L.integrals)
+    phi = df.Function(V)
+    res = df.action(form, phi)
+    assert not any(U._has_trial(i.integrand) for i in res.integrals)
+    split = U.test_function_split(sum((i.integrand for i in res.integrals), U.Const(0.0)), 1)
+    s, fx, fy = split[0]
+    assert not (isinstance(fx, U.Const) and fx.value == 0.0) and not (isinstance(fy, U.Const) and fy.value == 0.0)   # grad(u).grad(v)
+    assert not (isinstance(s, U.Const) and s.value == 0.0)                                                          # -f v
+
+
+def test_form_compiler_generates_and_cross_compiles_a_plugin(tmp_path, monkeypatch):
+    """UFL-lite -> CUDA source -> nvcc (sm_100a) -> .so exporting the plug-in entry points libfedmx dlopen()s; the cache key
+    covers the generated source and the library headers."""
+    from fedm_b200 import formcompiler as fc
+    df.parameters["form_compiler"]["quadrature_degree"] = None
+    form, u_new = _tof_form(df.RectangleMesh(df.Point(0, 0), df.Point(1, 1), 2, 2))
+    cf = fc.CompiledForm(form, u_new, None)
+    assert cf.n_eq == 1 and [g[:3] for g in cf.groups] == [("dx", None, 8)]
+    assert "QC0[25][4]" in cf.source and "struct JitModel" in cf.source and "dexp(" in cf.source
+    assert cf.key == fc.CompiledForm(form, u_new, None).key                       # deterministic
+    assert cf.key != fc.CompiledForm(form, u_new, 2).key                          # another quadrature rule = another kernel
+    monkeypatch.setattr(fc, "CACHE", tmp_path)
+    so = cf.build()
+    lib = ctypes.CDLL(str(so))
+    assert lib.fedmx_plugin_neq() == 1 and lib.fedmx_plugin_nf() == len(cf.fields)
+    assert hasattr(lib, "fedmx_plugin_launch") and lib.fedmx_plugin_args_size() > 0
+    assert cf.build() == so                                                       # second call hits the cache
