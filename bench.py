@@ -240,10 +240,15 @@ def main():
                                "mg_coarse": prof["mg_coarse"][1] / args.steps, "comm": prof["comm"][1] / args.steps},
         "roofline": {"kernel": "spmv_kernel<3,true,true> (SELL-32 block SpMV + node-block Jacobi + multigrid RHS extraction)", "bound": "hbm",
                      "achieved": spmv_gbs, "peak": peak, "unit": "GB/s", "frac": spmv_gbs / peak if spmv_gbs else None,
-                     "traffic": None, "peak_source": peak_src, "launches": n_sp,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch at n = 1825 on one GPU, from the committed
+                     # `ncu --set full` capture (profiles/r1_ncu_krylov_multigrid.txt); not re-measured per run
+                     "traffic": 2.006e9 if (world == 1 and args.n == FULL_N) else None,
+                     "peak_source": peak_src, "launches": n_sp,
                      "algorithmic_bytes_per_launch": spmv_b / world},
         "roofline_assembly": {"kernel": "assemble_rows_kernel<StreamerModel,true>", "bound": "hbm", "achieved": asm_gbs,
                               "peak": peak, "unit": "GB/s", "frac": asm_gbs / peak if asm_gbs else None,
+                              "traffic": 2.020e9 if (world == 1 and args.n == FULL_N) else None,   # profiles/r1_ncu_assemble_jacobian_v4.txt
+                              "fp64_pipe_active_frac": 0.53 if (world == 1 and args.n == FULL_N) else None,  # same capture: the kernel is FP64-issue bound
                               "launches": n_aj, "algorithmic_bytes_per_launch": asm_b / world},
         "e2e": {"value": args.steps / (ms_e2e * 1e-3), "unit": "steps/s",
                 "h2d_bytes_per_step": int(2 * 8 * dof), "d2h_bytes_per_step": int(8 * dof + 8)},
