@@ -18,7 +18,7 @@ from fedm.file_io import *                 # noqa: E402,F401,F403
 from fedm.functions import *               # noqa: E402,F401,F403
 
 
-def main(n=64, T_final=1e-10, input_dir=None, output_dir=None, linear_solver="gmres", max_steps=None):
+def main(n=64, T_final=1e-10, input_dir=None, output_dir=None, linear_solver="gmres", max_steps=None, mesh_file=None):
     if input_dir is not None:
         files.file_input = Path(input_dir)
     if output_dir is not None:
@@ -44,7 +44,8 @@ def main(n=64, T_final=1e-10, input_dir=None, output_dir=None, linear_solver="gm
     gamma = [0.0, 0.0]
     species_type = ["Ions", "electrons"]
 
-    mesh = RectangleMesh(Point(0.0, 0.0), Point(box, box), n, n)
+    # the reference reads an unstructured dolfin-XML mesh (fedm-streamer.py:116); without one, a structured grid of the same box
+    mesh = Mesh(str(mesh_file)) if mesh_file is not None else RectangleMesh(Point(0.0, 0.0), Point(box, box), n, n)
     facet_markers = Marking_boundaries(mesh, boundaries)
     normal = FacetNormal(mesh)
     dx = Measure("dx", domain=mesh)
@@ -137,8 +138,9 @@ def main(n=64, T_final=1e-10, input_dir=None, output_dir=None, linear_solver="gm
 if __name__ == "__main__":
     ap = ArgumentParser(description="FEDM streamer discharge on the B200 stack")
     ap.add_argument("--n", type=int, default=64)
+    ap.add_argument("--mesh", type=Path, default=None, help="dolfin-XML triangle mesh (the reference's mesh.xml); default: n x n grid")
     ap.add_argument("--input", type=Path, default=Path(__file__).resolve().parent.parent / "tests" / "golden" / "streamer_discharge_input")
     ap.add_argument("--output", type=Path, default=None)
     ap.add_argument("--t-final", type=float, default=1e-10)
     a = ap.parse_args()
-    main(n=a.n, T_final=a.t_final, input_dir=a.input, output_dir=a.output)
+    main(n=a.n, T_final=a.t_final, input_dir=a.input, output_dir=a.output, mesh_file=a.mesh)

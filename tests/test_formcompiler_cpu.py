@@ -105,3 +105,59 @@ def test_form_compiler_generates_and_cross_compiles_a_plugin(tmp_path, monkeypat
     assert lib.fedmx_plugin_neq() == 1 and lib.fedmx_plugin_nf() == len(cf.fields)
     assert hasattr(lib, "fedmx_plugin_launch") and lib.fedmx_plugin_args_size() > 0
     assert cf.build() == so                                                       # second call hits the cache
+
+
+def _write_dolfin_xml(path, coords, cells):
+    lines = ['<?xml version="1.0"?>', '<dolfin xmlns:dolfin="http://fenicsproject.org">', '  <mesh celltype="triangle" dim="2">',
+             f'    <vertices size="{len(coords)}">']
+    lines += [f'      <vertex index="{i}" x="{x!r}" y="{y!r}" />' for i, (x, y) in enumerate(coords.tolist())]
+    lines += ["    </vertices>", f'    <cells size="{len(cells)}">']
+    lines += [f'      <triangle index="{i}" v0="{a}" v1="{b}" v2="{c}" />' for i, (a, b, c) in enumerate(cells.tolist())]
+    lines += ["    </cells>", "  </mesh>", "</dolfin>"]
+    path.write_text("\n".join(lines))
+
+
+def test_dolfin_xml_mesh_reader_and_circle_boundaries(tmp_path):
+    """Mesh('mesh.xml') (fedm-streamer.py:116) and Marking_boundaries with a 'circle' entry (fedm/functions.py:86-124)."""
+    from fedm_b200.mesh import rectangle
+    tri = rectangle((0.0, 0.0), (1.0, 1.0), 6, 6, "crossed")
+    cells = tri.cells[:, ::-1].copy()                         # unsorted vertex order in the file: dolfin sorts on read
+    _write_dolfin_xml(tmp_path / "mesh.xml", tri.coords, cells)
+    mesh = df.Mesh(str(tmp_path / "mesh.xml"))
+    assert mesh.num_vertices() == tri.num_vertices and mesh.num_cells() == tri.num_cells
+    assert np.array_equal(mesh.coordinates(), tri.coords) and np.array_equal(mesh.cells(), np.sort(tri.cells, axis=1))
+    # bottom edge z = 0 as a line, and the unit circle around the origin clipped to z <= 0 (touches the boundary at (1, 0) only)
+    markers = F.Marking_boundaries(mesh, [["line", 0.0, 0.0, 0.0, 1.0], ["circle", 0.0, 0.0, 1.0]], gap_length=1.0)
+    vals = markers.array()
+    xy = mesh.coordinates()
+    mids = 0.5 * (xy[markers.facets[:, 0]] + xy[markers.facets[:, 1]])
+    assert set(np.unique(vals)) <= {0, 1, 2}
+    assert (vals[np.abs(mids[:, 1]) < 1e-14] == 1).all() and (vals[np.abs(mids[:, 1]) > 1e-14] == 0).all()
+    with pytest.raises(ValueError):
+        F.Marking_boundaries(mesh, [["ellipse", 0, 0, 1]])
+
+
+def test_streamer_script_runs_on_an_xml_mesh_like_on_the_generated_one(tmp_path, golden_dir, monkeypatch):
+    """The reference's own work flow -- a mesh.xml on disk -- through examples/streamer_discharge.py: identical to the run on
+    the equivalent generated mesh (numpy backend; the GPU run of the same script is tests/test_gpu_shim.py)."""
+    import sys
+    from pathlib import Path
+    from fedm_b200.mesh import rectangle
+    root = Path(__file__).resolve().parent.parent
+    for p in (str(root / "compat"), str(root / "examples")):
+        monkeypatch.syspath_prepend(p)
+    import dolfin
+    from oracle.ufl_backend import NumpyBackend
+    dolfin.set_backend(NumpyBackend())
+    import streamer_discharge as sd
+    n, box = 8, 0.0125
+    tri = rectangle((0.0, 0.0), (box, box), n, n, "right")
+    _write_dolfin_xml(tmp_path / "mesh.xml", tri.coords, tri.cells)
+    try:
+        kw = dict(input_dir=golden_dir / "streamer_discharge_input", linear_solver="mumps", max_steps=2)
+        u1, _ = sd.main(n=n, output_dir=tmp_path / "a", **kw)
+        u2, _ = sd.main(n=n, output_dir=tmp_path / "b", mesh_file=tmp_path / "mesh.xml", **kw)
+    finally:
+        sys.modules.pop("streamer_discharge", None)
+    assert np.array_equal(u1.vector()[:], u2.vector()[:])
+    assert (tmp_path / "a" / "relative error.log").read_text() == (tmp_path / "b" / "relative error.log").read_text()
