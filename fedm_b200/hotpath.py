@@ -323,7 +323,8 @@ class HotPath:
         handles = [None] * world
         dist.all_gather_object(handles, handle.raw)
         self._ck(self.lib.fedmx_peer_open(self.h, b"".join(handles)))
-        remote = np.array([plans[q][1][plans[q][0].index(rank)] for q in nb], dtype=np.int32)
+        from .partition import peer_staging_offsets
+        remote = np.array(peer_staging_offsets(rank, plans), dtype=np.int32)
         self._ck(self.lib.fedmx_peer_halo_set(self.h, len(nb), _np_ptr(remote)))
         dist.barrier()
 

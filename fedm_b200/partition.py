@@ -85,3 +85,11 @@ def build_local_mesh(coords, cells, facet_vertices, facet_markers, owner, rank, 
     return LocalMesh(rank, world, np.ascontiguousarray(coords[l2g]), lcells, owned.size, l2g, lfv, lfm,
                      np.asarray(neighbors, dtype=np.int32), np.asarray(send_ptr, dtype=np.int32), cat(send_nodes),
                      np.asarray(recv_ptr, dtype=np.int32), cat(recv_nodes), n, cells.shape[0])
+
+
+def peer_staging_offsets(rank, plans):
+    """For the NVLink peer-memory transport (fedmx_peer_halo_set): `plans[q] = (neighbor ranks of q, recv_ptr of q)` for every
+    rank q; returns, per neighbour of `rank` in its own neighbour order, the node offset of `rank`'s segment inside THAT
+    neighbour's receive staging buffer (= the neighbour's recv_ptr entry for `rank`)."""
+    mine = plans[rank][0]
+    return [int(plans[q][1][list(plans[q][0]).index(rank)]) for q in mine]

@@ -95,3 +95,26 @@ def test_halo_plan_world2_gloo():
         p.join(120)
         assert p.exitcode == 0
     assert list(ok) == [1] * world
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_peer_staging_offsets_put_every_segment_where_the_receiver_unpacks_it(world):
+    """Host logic of the NVLink peer-memory transport (fedmx_peer_halo_set): a numpy emulation of the push (sender writes its
+    segment at the remote offset of the receiver's staging buffer) followed by the receiver's unpack must equal the owners'
+    values at every ghost node."""
+    from fedm_b200.partition import peer_staging_offsets
+    m, locs, owner = parts(world, "right", n=11)
+    plans = [([int(q) for q in lm.neighbors], [int(v) for v in lm.recv_ptr]) for lm in locs]
+    gvals = np.random.default_rng(world).normal(size=m.num_vertices)
+    staging = [np.full(lm.recv_ptr[-1], np.nan) for lm in locs]
+    for lm in locs:                                                       # push
+        offs = peer_staging_offsets(lm.rank, plans)
+        local = gvals[lm.local_to_global]
+        for i, q in enumerate(lm.neighbors):
+            seg = local[lm.send_nodes[lm.send_ptr[i]:lm.send_ptr[i + 1]]]
+            staging[q][offs[i]:offs[i] + seg.size] = seg
+    for lm in locs:                                                       # unpack
+        assert not np.isnan(staging[lm.rank]).any()
+        vec = np.zeros(lm.num_vertices)
+        vec[lm.recv_nodes] = staging[lm.rank]
+        assert np.array_equal(vec[lm.n_owned:], gvals[lm.local_to_global[lm.n_owned:]])
