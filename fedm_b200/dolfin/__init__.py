@@ -171,6 +171,13 @@ def RectangleMesh(p0, p1, nx, ny, diagonal="right"):
     return Mesh(rectangle((p0[0], p0[1]), (p1[0], p1[1]), nx, ny, diagonal))
 
 
+def IntervalMesh(n, a, b):
+    """1-D meshes (examples/time_of_flight_1D of the reference, P2 interval elements) are outside the device path: the row kernels
+    are P1 triangles.  The configuration is covered by the CPU oracle (oracle/tof1d.py, tests/test_oracle_tof1d.py)."""
+    raise NotImplementedError("dolfin shim: IntervalMesh / 1-D elements are not part of the B200 hot path (P1 triangles only); "
+                              "the 1-D time-of-flight case is covered by the CPU oracle oracle/tof1d.py")
+
+
 class MeshFunction:
     """Only the case FEDM uses: a size_t function over facets (dim-1) holding the markers of the exterior facets."""
 
