@@ -1,8 +1,8 @@
 """Pre-compile the form-compiler plug-ins that the examples and the GPU tests use (CPU container: nvcc cross-compiles sm_100a).
 
-The scripts are executed at tiny size on the oracle's numpy backend (test infrastructure: here it only drives the scripts so
-that every form they hand to the backend is seen); each form is lowered by fedm_b200.formcompiler and built into
-fedm_b200/jit_cache/, where the GPU box finds it by hash (source + library headers) instead of running nvcc at test time."""
+The scripts are executed at tiny size on the shim's dry-run backend (fedm_b200/dolfin/dryrun_backend.py: no solve happens, the
+forms are only collected); each form is lowered by fedm_b200.formcompiler and built into fedm_b200/jit_cache/, where the GPU box
+finds it by hash (source + library headers) instead of running nvcc at test time."""
 import sys
 import tempfile
 import time
@@ -14,19 +14,11 @@ sys.path[:0] = [str(ROOT), str(ROOT / "compat"), str(ROOT / "examples"), str(ROO
 
 def main():
     import dolfin
-    from fedm_b200.formcompiler import CompiledForm
-    from oracle.ufl_backend import NumpyBackend
+    from fedm_b200.dolfin.dryrun_backend import DryRunBackend
 
-    built = []
-
-    class Recorder(NumpyBackend):
-        def compile(self, residual, u, bcs, quad_degree, ident_zeros=False):
-            t0 = time.time()
-            so = CompiledForm(residual, u, quad_degree).build()
-            built.append((so.name, time.time() - t0))
-            return super().compile(residual, u, bcs, quad_degree, ident_zeros=ident_zeros)
-
-    dolfin.set_backend(Recorder())
+    backend = DryRunBackend()
+    t_start = time.time()
+    dolfin.set_backend(backend)
     golden = ROOT / "tests" / "golden"
     try:
         with tempfile.TemporaryDirectory() as tmp:
@@ -45,14 +37,14 @@ def main():
     finally:
         dolfin.set_backend(None)
         dolfin.parameters["form_compiler"]["quadrature_degree"] = None
-    names = sorted({b[0] for b in built})
+    names = sorted(set(backend.built))
     # drop plug-ins of older library headers (their hash can no longer be requested)
     cache = ROOT / "fedm_b200" / "jit_cache"
     keep = {Path(n).stem for n in names}
     for f in cache.glob("form_*"):
         if f.stem not in keep and f.suffix in (".so", ".cu"):
             f.unlink()
-    print(f"prebuilt {len(names)} form plug-ins in {sum(b[1] for b in built):.1f} s:", ", ".join(names))
+    print(f"prebuilt {len(names)} form plug-ins in {time.time() - t_start:.1f} s:", ", ".join(names))
 
 
 if __name__ == "__main__":
