@@ -17,7 +17,11 @@ variable-step BDF2 in log-density form) and is *pinned* against the reference's 
 
 The streamer case has no mesh and no golden densities in the checkout
 (``.MISSING_LARGE_BLOBS``): its oracle is built from the same code path as the two pinned
-cases and is "parity unpinned" for the assembled entries themselves.
+cases and is "parity unpinned" for the assembled entries themselves; it is cross-checked by
+executing the reference's UNMODIFIED streamer script (its own form-building code) on a generated
+mesh through the shim's numpy backend (tests/test_shim_reference_scripts.py).  The 1-D time of
+flight (BASELINE configs[0], ``tof1d.py``) has no fixture either: "parity unpinned", anchored on
+its exact solution (tests/test_oracle_tof1d.py).
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs may import
 this package -- always as the checker / the reported baseline, never as the product path.
