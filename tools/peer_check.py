@@ -12,6 +12,7 @@ import torch.distributed as dist
 
 from fedm_b200.streamer import StreamerCase
 
+os.environ["FEDMX_PEER"] = "1"          # the peer-memory transport is opt-in (NCCL is the default): create the heap for this check
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
