@@ -1,5 +1,7 @@
-"""The reference's UNMODIFIED ``fedm`` package and UNMODIFIED integrated-test scripts executed on this repo's dolfin shim
-(``compat/dolfin`` -> ``fedm_b200.dolfin`` + UFL-lite) with the oracle's numpy backend, compared with the reference's goldens.
+"""The reference's UNMODIFIED integrated-test scripts executed on this repo's dolfin shim (``compat/dolfin`` ->
+``fedm_b200.dolfin`` + UFL-lite) with the oracle's numpy backend, compared with the reference's goldens -- once with the
+reference's own UNMODIFIED ``fedm`` package (``/root/reference`` ahead of ``compat/`` on sys.path: validates the shim alone) and
+once with this repo's API mirror (``compat/fedm`` -> ``fedm_b200.functions`` / ``file_io``: validates the mirror as well).
 This validates the shim semantics (form capture, UFL degree estimation, Expression interpolation, project, assigners,
 boundary conditions, file_output) on the CPU; the same shim drives the CUDA backend on the GPU box
 (tests/test_gpu_shim.py).  Needs /root/reference (present in the build container only) -- skipped elsewhere."""
@@ -17,13 +19,19 @@ ROOT = Path(__file__).resolve().parent.parent
 pytestmark = pytest.mark.skipif(not (REF / "fedm" / "functions.py").exists(), reason="reference checkout not available")
 
 
-@pytest.fixture()
-def shim_env(monkeypatch):
-    for p in (str(REF), str(ROOT / "compat")):
+@pytest.fixture(params=["reference-fedm", "mirror-fedm"])
+def shim_env(monkeypatch, request):
+    # syspath_prepend puts the LAST call first: `fedm` resolves to the first of /root/reference and compat/ on the path,
+    # `dolfin` always to compat/dolfin (the reference has no dolfin)
+    order = (str(ROOT / "compat"), str(REF)) if request.param == "reference-fedm" else (str(REF), str(ROOT / "compat"))
+    for p in order:
         monkeypatch.syspath_prepend(p)
     for name in [m for m in sys.modules if m == "dolfin" or m == "fedm" or m.startswith("fedm.")]:
         monkeypatch.delitem(sys.modules, name)
     import dolfin
+    import fedm.functions
+    expect = str(REF) if request.param == "reference-fedm" else str(ROOT / "compat")
+    assert fedm.functions.__file__.startswith(expect), fedm.functions.__file__
     from oracle.ufl_backend import NumpyBackend
     dolfin.set_backend(NumpyBackend())
     yield dolfin
