@@ -122,6 +122,7 @@ def main():
     ap.add_argument("--n", type=int, default=FULL_N, help="grid size (n x n cells pairs); 1825 -> 10.0M DOF")
     ap.add_argument("--sample-n", type=int, default=0, help="CPU-baseline sample grid (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the post-run parity trajectory (1-GPU / exact-solve re-run)")
     ap.add_argument("--profile-detail", action="store_true", help="nested event timing of multigrid levels and collectives")
     args = ap.parse_args()
 
@@ -186,6 +187,9 @@ def main():
     stats = case.stats[n_stats0:]
     newton_its = sum(s[0] for s in stats)
     krylov_its = sum(s[1] for s in stats)
+    # state after warmup + K accepted steps, global vertex order (gathered over the ranks): input of the parity check below
+    x_timed = case.gather_state().clone()
+    steps_taken = args.warmup + args.steps
 
     # ---- end-to-end: same steps through the host-buffer API (H2D of the three state vectors, D2H of the result)
     hb = case.make_host_buffers()
@@ -206,8 +210,30 @@ def main():
 
     if rank != 0:
         if world > 1:
+            dist.barrier()                        # rank 0 runs the 1-GPU parity trajectory meanwhile
             dist.destroy_process_group()
         return 0
+
+    # ---- parity of what was timed (outside every timed region).  One GPU: the same code with exact linear solves
+    # (ksp_rtol 1e-13 = the examples' 'mumps' semantics) for the same number of steps; N GPUs: the un-partitioned run.
+    parity = None
+    if not args.no_parity:
+        kw = dict(ksp_rtol=1e-13, ksp_max_it=50000) if world == 1 else {}
+        ref_case = StreamerCase(n=args.n, device=local_rank, **kw)
+        ref_case.set_initial_state(bench_initial_potential=True)
+        ref_case.run(max_steps=steps_taken)
+        Xr = ref_case.x_new.view(-1, 3)
+        rel = [float((x_timed[:, k] - Xr[:, k]).abs().max() / Xr[:, k].abs().max()) for k in range(3)]
+        dts = [r[2] for r in case.rows[:steps_taken]]
+        dts_ref = [r[2] for r in ref_case.rows[:steps_taken]]
+        parity = {"against": "same code, ksp_rtol=1e-13 (exact linear solves), 1 GPU" if world == 1 else
+                             "un-partitioned 1-GPU run, same solver semantics",
+                  "steps": steps_taken, "max_rel_diff": max(rel), "per_component": rel,
+                  "dt_sequence_max_rel_diff": max(abs(a / b - 1.0) for a, b in zip(dts, dts_ref)),
+                  "newton_counts_equal": [s_[0] for s_ in case.stats[:steps_taken]] == [s_[0] for s_ in ref_case.stats[:steps_taken]],
+                  "krylov_its_per_step_ref": sum(s_[1] for s_ in ref_case.stats) / max(1, steps_taken)}
+        ref_case.hot.close()
+        del ref_case
 
     peak, peak_src = peaks()
     asm_b, spmv_b, nnz = algorithmic_bytes(nv, nc)
@@ -253,6 +279,7 @@ def main():
         "e2e": {"value": args.steps / (ms_e2e * 1e-3), "unit": "steps/s",
                 "h2d_bytes_per_step": int(2 * 8 * dof), "d2h_bytes_per_step": int(8 * dof + 8)},
         "gpu_launches": launches, "clocks": clk, "setup_s": setup_s,
+        "parity" if world == 1 else "parity_vs_1gpu": parity,
     }
     if not args.no_cpu_baseline and world == 1:
         try:
@@ -264,6 +291,7 @@ def main():
             line["cpu_baseline"] = {"value": None, "unit": "steps/s", "cores": 0, "kind": "port", "sample": f"failed: {exc}"}
     print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
     return 0
 

@@ -349,6 +349,7 @@ static const bool kGridFuse = getenv("FEDMX_MG_FUSE") && std::string(getenv("FED
 static const int64_t kGridFuseRows = getenv("FEDMX_GRID_FUSE_ROWS") ? atoll(getenv("FEDMX_GRID_FUSE_ROWS")) : 1000000;
 
 static int setup_coarse_fusion(fedmx_ctx *ctx) {
+    PoolScope pool(ctx, &ctx->amg_device);
     auto &L = ctx->amg_levels;
     const int nl = int(L.size());
     int first = nl - 1;
@@ -495,7 +496,9 @@ int fedmx_precond_apply(fedmx_ctx *ctx, const double *d_r, double *d_z) {
     } else {
         const unsigned nb = unsigned((n + threads - 1) / threads);
         switch (ctx->n_eq) {
+            case 2: dinv_extract_kernel<2><<<nb, threads, 0, ctx->stream>>>(ctx->sell, ctx->d_dinv, d_r, comp, d_z, l0.b); break;
             case 3: dinv_extract_kernel<3><<<nb, threads, 0, ctx->stream>>>(ctx->sell, ctx->d_dinv, d_r, comp, d_z, l0.b); break;
+            case 4: dinv_extract_kernel<4><<<nb, threads, 0, ctx->stream>>>(ctx->sell, ctx->d_dinv, d_r, comp, d_z, l0.b); break;
             case 5: dinv_extract_kernel<5><<<nb, threads, 0, ctx->stream>>>(ctx->sell, ctx->d_dinv, d_r, comp, d_z, l0.b); break;
             default: ctx->err = "two-stage preconditioner: unsupported n_eq"; return FEDMX_EUNSUPPORTED;
         }
@@ -522,8 +525,13 @@ extern "C" int fedmx_pc_apply(fedmx_ctx *ctx, const double *d_r, double *d_z) {
 
 extern "C" int fedmx_amg_reset(fedmx_ctx *ctx) {
     if (!ctx) return FEDMX_EINVAL;
-    ctx->amg_levels.clear();      // device memory stays owned by the context until destroy
+    cudaStreamSynchronize(ctx->stream);
+    for (void *p : ctx->amg_device) cudaFree(p);      // a second set-up (new mesh marks, new block) must not leak the first
+    ctx->amg_device.clear();
+    ctx->amg_levels.clear();
     ctx->amg_coarse_inv = nullptr;
+    ctx->d_coarse_levels = nullptr;
+    ctx->d_grid_barrier = nullptr;
     ctx->precond_kind = 0;
     ctx->coarse_first = -1;
     ctx->coarse_count = 0;
@@ -538,6 +546,7 @@ extern "C" int fedmx_amg_add_level(fedmx_ctx *ctx, int64_t n, const double *h_di
     FEDMX_REQUIRE(ctx, n > 0 && h_dinv, "fedmx_amg_add_level: bad level");
     FEDMX_REQUIRE(ctx, !ctx->amg_levels.empty() || n == ctx->n_owned, "fedmx_amg_add_level: finest level must have n_owned rows");
     FEDMX_REQUIRE(ctx, ctx->amg_levels.empty() || ctx->amg_levels.back().n_coarse == n, "fedmx_amg_add_level: level sizes do not chain");
+    PoolScope pool(ctx, &ctx->amg_device);
     AmgLevel lv{};
     lv.n = n;
     lv.n_coarse = n_coarse;
@@ -575,6 +584,7 @@ extern "C" int fedmx_amg_set_coarse(fedmx_ctx *ctx, int n, const double *h_inver
                   "fedmx_amg_set_coarse: the last level must be the coarsest one");
     FEDMX_REQUIRE(ctx, n <= 8192, "fedmx_amg_set_coarse: coarsest level too large");
     std::vector<double> m(h_inverse, h_inverse + size_t(n) * n);
+    PoolScope pool(ctx, &ctx->amg_device);
     return fedmx_upload(ctx, &ctx->amg_coarse_inv, m);
 }
 

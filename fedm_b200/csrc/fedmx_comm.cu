@@ -63,6 +63,15 @@ extern "C" int fedmx_comm_init(fedmx_ctx *ctx, int n_ranks, int rank, const char
     return FEDMX_OK;
 }
 
+// one communicator per context: released with it (a context per Poisson_solver / project call would leak one each otherwise)
+int fedmx_comm_destroy_internal(fedmx_ctx *ctx) {
+    if (ctx->nccl_comm) {
+        ncclCommDestroy((ncclComm_t)ctx->nccl_comm);
+        ctx->nccl_comm = nullptr;
+    }
+    return FEDMX_OK;
+}
+
 extern "C" int fedmx_halo_set(fedmx_ctx *ctx, int n_neighbors, const int32_t *h_neighbor_ranks, const int32_t *h_send_ptr,
                               const int32_t *h_send_nodes, const int32_t *h_recv_ptr, const int32_t *h_recv_nodes) {
     if (!ctx) return FEDMX_EINVAL;

@@ -25,7 +25,9 @@ extern "C" int fedmx_ctx_destroy(fedmx_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     fedmx_peer_destroy(ctx);
+    fedmx_comm_destroy_internal(ctx);
     for (void *p : ctx->owned_device) cudaFree(p);
+    for (void *p : ctx->amg_device) cudaFree(p);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     for (auto &pool : ctx->prof_ev)
         for (cudaEvent_t e : pool) cudaEventDestroy(e);

@@ -117,6 +117,8 @@ struct fedmx_ctx {
     double *d_coords = nullptr;  // [n_vertices][2]
     SellView sell{};
     std::vector<void *> owned_device;   // everything cudaMalloc'ed by set-up calls
+    std::vector<void *> amg_device;     // multigrid hierarchy: released by fedmx_amg_reset (re-running set-up must not leak)
+    std::vector<void *> *alloc_pool = nullptr;   // where fedmx_dev_alloc records (default: owned_device)
     // host copies for pattern export
     std::vector<int32_t> h_rowptr, h_colidx;      // node-block CSR of the owned rows
     std::vector<int32_t> h_slice_ptr;
@@ -190,10 +192,17 @@ int fedmx_dev_alloc(fedmx_ctx *ctx, T **ptr, size_t count) {
         ctx->err = std::string("cudaMalloc: ") + cudaGetErrorString(e);
         return FEDMX_ENOMEM;
     }
-    ctx->owned_device.push_back(p);
+    (ctx->alloc_pool ? ctx->alloc_pool : &ctx->owned_device)->push_back(p);
     *ptr = (T *)p;
     return FEDMX_OK;
 }
+
+// RAII: allocations inside the scope are recorded in `pool` (e.g. the multigrid hierarchy's own list)
+struct PoolScope {
+    fedmx_ctx *c;
+    PoolScope(fedmx_ctx *ctx, std::vector<void *> *pool) : c(ctx) { c->alloc_pool = pool; }
+    ~PoolScope() { c->alloc_pool = nullptr; }
+};
 
 template <class T>
 int fedmx_upload(fedmx_ctx *ctx, T **ptr, const std::vector<T> &h) {
@@ -223,4 +232,5 @@ int fedmx_precond_apply(fedmx_ctx *ctx, const double *d_r, double *d_z);
 int fedmx_peer_halo_exchange(fedmx_ctx *ctx, double *d_vec, int n_comp);
 int fedmx_peer_allreduce(fedmx_ctx *ctx, double *d_buf, int64_t n);
 int fedmx_peer_destroy(fedmx_ctx *ctx);
+int fedmx_comm_destroy_internal(fedmx_ctx *ctx);
 double *fedmx_peer_big_buffer(fedmx_ctx *ctx, int64_t n);

@@ -849,8 +849,12 @@ class File:
 
 
 class XDMFFile:
-    """Checkpoint writer.  No HDF5 library is available in this environment, so checkpoints go to ``<name>.npz``
-    (arrays ``<name>_<k>`` in vertex order plus their times)."""
+    """``XDMFFile(comm, 'dir/name.xdmf').write_checkpoint(f, name, t, XDMFFile.Encoding.HDF5, append)`` (reference:
+    fedm/file_io.py:594-600, fedm_gd.py:271): real HDF5 next to the XDMF index, in dolfin's layout
+    ``/<name>/<name>_<k>/{mesh/topology, mesh/geometry, cell_dofs, x_cell_dofs, cells, vector}`` with ``vector`` and
+    ``cell_dofs`` in dolfin's own (SCOTCH-GPS) dof numbering, so the reference's readers (testing_utils.read_h5) and its
+    entry-by-entry comparison with FEniCS output work unchanged.  Containers are written by fedm_b200/hdf5_lite.py (no HDF5
+    library in this image); appending never rewrites or keeps earlier snapshots in memory."""
 
     class Encoding:
         HDF5 = "HDF5"
@@ -859,17 +863,61 @@ class XDMFFile:
     def __init__(self, *args):
         self.path = Path(str(args[-1]))
         self.parameters = _Params()
-        self.data = {}
+        self._grids = {}                 # name -> list of (k, t, n_cells, n_vertices)
+        self._h5 = None
+        self._v2d = {}                   # id(mesh arrays) -> vertex-to-dof map (GPS numbering is O(mesh), computed once)
 
     def write_checkpoint(self, f, name, t=0.0, encoding=None, append=False):
-        k = sum(1 for key in self.data if key.startswith(name + "_") and not key.endswith("_t"))
-        self.data[f"{name}_{k}"] = f.vector().get_local()
-        self.data[f"{name}_{k}_t"] = np.array(t)
+        from ..dofmap import checkpoint_datasets, fenics_vertex_to_dof
+        from ..hdf5_lite import H5CheckpointFile
+        if encoding not in (None, XDMFFile.Encoding.HDF5):
+            raise ValueError("XDMFFile.write_checkpoint: only Encoding.HDF5 is implemented")
+        space = f.function_space()
+        if space.n_comp != 1:
+            raise ValueError("XDMFFile.write_checkpoint: scalar P1 functions only (FEDM writes one file per species)")
+        tri = space.mesh().tri
+        key = (id(tri.cells), tri.num_vertices)
+        if key not in self._v2d:
+            self._v2d[key] = fenics_vertex_to_dof(tri.cells, tri.num_vertices)
+        if self._h5 is None:
+            self._h5 = H5CheckpointFile(self.path.with_suffix(".h5"))
+        if not append:
+            self._grids.pop(name, None)
+            if len(self._grids) == 0:
+                self._grids = {}
+        data = checkpoint_datasets(tri.coords, tri.cells, f.vector().get_local(), self._v2d[key])
+        k = self._h5.add_checkpoint(name, data, append=bool(append))
+        self._grids.setdefault(name, []).append((k, float(t), tri.num_cells, tri.num_vertices))
+        self._write_xdmf()
+
+    def _write_xdmf(self):
+        h5 = self.path.with_suffix(".h5").name
+        out = ['<?xml version="1.0"?>', '<!DOCTYPE Xdmf SYSTEM "Xdmf.dtd" []>',
+               '<Xdmf Version="3.0" xmlns:xi="http://www.w3.org/2001/XInclude">', "  <Domain>"]
+        for name, grids in self._grids.items():
+            out.append(f'    <Grid Name="{name}" GridType="Collection" CollectionType="Temporal">')
+            for k, t, nc, nv in grids:
+                g = f"{h5}:/{name}/{name}_{k}"
+                out += [f'      <Grid Name="{name}_{k}" GridType="Uniform">',
+                        f'        <Topology NumberOfElements="{nc}" TopologyType="Triangle" NodesPerElement="3">',
+                        f'          <DataItem Dimensions="{nc} 3" NumberType="UInt" Format="HDF">{g}/mesh/topology</DataItem>',
+                        "        </Topology>", '        <Geometry GeometryType="XY">',
+                        f'          <DataItem Dimensions="{nv} 2" Format="HDF">{g}/mesh/geometry</DataItem>', "        </Geometry>",
+                        f'        <Time Value="{t!r}" />',
+                        f'        <Attribute ItemType="FiniteElementFunction" ElementFamily="CG" ElementDegree="1" '
+                        f'ElementCell="triangle" Name="{name}" Center="Other" AttributeType="Scalar">',
+                        f'          <DataItem Dimensions="{3 * nc} 1" NumberType="UInt" Format="HDF">{g}/cell_dofs</DataItem>',
+                        f'          <DataItem Dimensions="{nv} 1" Format="HDF">{g}/vector</DataItem>',
+                        f'          <DataItem Dimensions="{nc + 1} 1" NumberType="UInt" Format="HDF">{g}/x_cell_dofs</DataItem>',
+                        f'          <DataItem Dimensions="{nc} 1" NumberType="UInt" Format="HDF">{g}/cells</DataItem>',
+                        "        </Attribute>", "      </Grid>"]
+            out.append("    </Grid>")
+        out += ["  </Domain>", "</Xdmf>", ""]
         self.path.parent.mkdir(parents=True, exist_ok=True)
-        np.savez(self.path.with_suffix(".npz"), **self.data)
+        self.path.write_text("\n".join(out))
 
     def write(self, *args):
-        pass
+        raise NotImplementedError("XDMFFile.write (plain mesh/function output) is not used by FEDM; use write_checkpoint or File('*.pvd')")
 
     def close(self):
         pass

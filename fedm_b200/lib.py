@@ -33,6 +33,9 @@ SIGNATURES = {
                                  C.c_void_p, C.c_void_p, C.c_int64]),
     "fedmx_pattern_get": (C.c_int, [C.c_void_p, c_i64p, c_i64p, C.c_void_p, C.c_void_p]),
     "fedmx_matrix_get_bsr": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "fedmx_gps_numbering": (C.c_int, [C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "fedmx_dofmap_fenics": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "fedmx_pattern_get_fenics": (C.c_int, [C.c_void_p, c_i64p, c_i64p, C.c_void_p, C.c_void_p]),
     "fedmx_dirichlet_set": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
     "fedmx_model_set": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "fedmx_plugin_load": (C.c_int, [C.c_void_p, C.c_char_p]),

@@ -253,6 +253,19 @@ class StreamerCase:
         self.max_error[1] = self.max_error[0]
         return attempts
 
+    def gather_state(self, x=None):
+        """(n_global_vertices, 3) state in GLOBAL vertex order on every rank (what `Function.vector().gather()` / a serial
+        output writer sees); the identity on one GPU."""
+        x = self.x_new if x is None else x
+        if self.world == 1:
+            return x.view(-1, 3)
+        import torch.distributed as dist
+        lm = self.local
+        full = torch.zeros((lm.n_global_vertices, 3), dtype=torch.float64, device=x.device)
+        full[torch.from_numpy(lm.local_to_global[:lm.n_owned]).to(x.device)] = x.view(-1, 3)[:lm.n_owned]
+        dist.all_reduce(full)
+        return full
+
     def run(self, T_final=1e-10, max_steps=None):
         steps = 0
         while self.t < T_final * (1 + 1e-6):

@@ -4,7 +4,10 @@ Mirrors the control flow of ``fedm.functions.adaptive_solver`` / ``adaptive_time
 (fedm/functions.py:915-927, 958-1130): attempt, estimate, log a row of ``relative error.log``, accept or shrink
 and retry, ``SystemExit`` below ``dt_min``.  The heavy work of every attempt is one call into libfedmx.
 """
+import sys
+
 from . import hotpath as _hp
+from .lib import FedmxError
 
 
 class ErrorGreaterThanTTOL(Exception):
@@ -30,10 +33,16 @@ def attempt_until_accepted(solve_attempt, reset, t, dt, dt_old, ttol, dt_min, ma
             if err >= ttol:
                 raise ErrorGreaterThanTTOL
             return t_new, dt, attempts
+        except FedmxError:
+            # a library failure (CUDA / NCCL / peer-transport error, bad argument) is not a solver failure: retrying with a
+            # smaller step would only hide it -- and would desynchronise the ranks of a partitioned run.  Fatal.
+            raise
         except Exception as exc:                      # same catch-all as the reference (fedm/functions.py:1080)
             if isinstance(exc, ErrorGreaterThanTTOL):
                 dt = dt * (0.5 * ttol / max_error[0])
             else:
+                print(f"[fedm_b200] attempt with dt = {dt:g} failed ({type(exc).__name__}: {exc}); halving the step",
+                      file=sys.stderr, flush=True)
                 dt = dt * 0.5
             if dt < dt_min:
                 raise SystemExit("Minimum time-step size reached, program is terminating.")

@@ -81,6 +81,15 @@ int fedmx_mesh_set(fedmx_ctx *ctx, int n_eq, int64_t n_vertices, const double *h
 /* Pattern queries (node-block CSR of the owned rows; expands to dolfin's scalar pattern with
  * dof = n_eq*node+comp).  Call with NULL arrays to get sizes. */
 int fedmx_pattern_get(fedmx_ctx *ctx, int64_t *n_rows, int64_t *nnz_blocks, int32_t *h_rowptr, int32_t *h_colidx);
+/* FEniCS 2019.1.0 numbering as an export permutation.  dolfin numbers the dofs of a serial P1 space with SCOTCH's
+ * Gibbs-Poole-Stockmeyer ordering (DofMapBuilder behind `FunctionSpace(mesh, 'P', 1)`, fedm_gd.py:116-123); everything the
+ * reference stores in dof order (the checkpoints of fedm/file_io.py:594-600, compared in
+ * tests/integrated_tests/glow_discharge/test_glow_discharge.py:53-62) depends on it.  Mixed spaces: dof = n_eq*d + comp.
+ * fedmx_gps_numbering is context-free host code: adjacency graph in CSR form (ascending neighbours) -> dof-to-vertex map. */
+int fedmx_gps_numbering(int64_t n, const int32_t *h_rowptr, const int32_t *h_colidx, int32_t start, int32_t *h_dof_to_vertex);
+int fedmx_dofmap_fenics(fedmx_ctx *ctx, int32_t *h_dof_to_vertex);
+/* dolfin's scalar SparsityPattern in dolfin's own dof numbering (rows/columns n_eq*dof+comp, ascending columns). */
+int fedmx_pattern_get_fenics(fedmx_ctx *ctx, int64_t *n_rows, int64_t *nnz, int64_t *h_rowptr, int32_t *h_colidx);
 /* Copy the assembled Jacobian out as block CSR values [nnz_blocks][n_eq][n_eq] (host buffer). */
 int fedmx_matrix_get_bsr(fedmx_ctx *ctx, double *h_values);
 
@@ -91,7 +100,7 @@ int fedmx_dirichlet_set(fedmx_ctx *ctx, int comp, int64_t n_nodes, const int32_t
 /* ---- model (the "form compiler" output) ---------------------------------------------------------- */
 /* Replaces UFL form construction + FFC/dijitso JIT of `F = action(F,u_new); J = derivative(F,u_new,u)`
  * (fedm_streamer.py:296-297): selects the hand-written cell/facet kernel family and its constants.
- * h_params: model-specific double array (see fedm_b200/models.py for the layouts). */
+ * h_params: model-specific double array (layouts: the header comment of each model in fedm_b200/csrc/fedmx_assemble.cu and glow_model.cuh; host side: fedm_b200/streamer.py STREAMER_PARAMS, fedm_b200/glow.py). */
 int fedmx_model_set(fedmx_ctx *ctx, int model_id, int n_params, const double *h_params);
 /* Run-time compiled forms -- the role of FFC + dijitso for `F = action(F,u_new); J = derivative(F,u_new,u)` with arbitrary
  * user forms (fedm_streamer.py:296-297): fedm_b200/formcompiler.py lowers a UFL-lite form to CUDA source for the generic
