@@ -96,17 +96,28 @@ def algorithmic_bytes(nv, nc, n_eq=3, zero_entries=1):
     return asm, spmv, nnz
 
 
+def workload_config(n):
+    """The workload both arms run -- identical dict in the GPU line and in the `--impl reference` line."""
+    nv, nc = (n + 1) ** 2, 2 * n * n
+    return {"workload": f"synthetic streamer mesh n={n} (right grid), one accepted BDF2 step, Newton rtol 1e-4, GMRES(30) rtol 1e-5 "
+                        "(reference test semantics)",
+            "dof": 3 * nv, "cells": nc, "nnz": 9 * (nv + 2 * (nv + nc - 1)), "l2": "inputs larger than L2 (no flush)"}
+
+
 # ---------------------------------------------------------------------------------------------------------
 def run_reference(args):
-    """CPU arm: the oracle port (C/OpenMP restatement when built, else the numpy oracle) on a bounded sample."""
+    """CPU arm: the compiled restatement of the reference's path (oracle/csrc) on all host cores, on the bench mesh itself."""
     from oracle import cpu_baseline
-    res = cpu_baseline.run(steps=args.steps, warmup=args.warmup, full_n=args.n, sample_n=args.sample_n)
+    res = cpu_baseline.full(steps=args.steps, warmup=args.warmup, n=args.n, budget_s=args.ref_budget_s)
     line = {"impl": "reference", "metric": "streamer BDF2 steps/s (synthetic 10.0M-DOF mesh)", "value": res["value"],
-            "unit": "steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "unit": "steps/s", "n_gpus": args.gpus, "steps": res["timed_steps"], "warmup": res["warmup_done"],
+            "steps_requested": args.steps, "warmup_requested": args.warmup,
             "ms_per_step": 1e3 / res["value"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"synthetic streamer mesh n={args.n} (right grid), BDF2 step, Newton rtol 1e-4, "
-                                   "GMRES(30) rtol 1e-5", "dof": 3 * (args.n + 1) ** 2},
+            "dtype": "f64", "data": "synthetic", "config": workload_config(args.n),
+            "solver": {"linear": "GMRES(30), classical Gram-Schmidt, left PC, rtol 1e-5", "preconditioner": "block Jacobi (one block per "
+                       "thread) + ILU(0) -- PETSc's default under mpirun", "newton_its_per_step": res["newton_its_per_step"],
+                       "krylov_its_per_step": res["krylov_its_per_step"], "phase_seconds_total": res["phase_seconds_total"],
+                       "setup_s": res["setup_s"]},
             "cpu_baseline": {"value": res["value"], "unit": "steps/s", "cores": res["cores"], "kind": res["kind"],
                              "sample": res["sample"]},
             "e2e": {"value": res["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -120,7 +131,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="fedm_b200")
     ap.add_argument("--n", type=int, default=FULL_N, help="grid size (n x n cells pairs); 1825 -> 10.0M DOF")
-    ap.add_argument("--sample-n", type=int, default=0, help="CPU-baseline sample grid (0 = auto)")
+    ap.add_argument("--ref-budget-s", type=float, default=200.0, help="wall-clock budget of the CPU arm's timed steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the post-run parity trajectory (1-GPU / exact-solve re-run)")
     ap.add_argument("--profile-detail", action="store_true", help="nested event timing of multigrid levels and collectives")
@@ -250,9 +261,9 @@ def main():
         "value": args.steps / (ms * 1e-3), "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"synthetic streamer mesh n={args.n} (right grid), BDF2 step, Newton rtol 1e-4, "
-                               "GMRES(30) rtol 1e-5 (reference test semantics), two-stage AMG(Phi)+block-Jacobi preconditioner",
-                   "dof": dof, "cells": nc, "nnz": nnz, "l2": "inputs larger than L2 (no flush)",
+        "config": workload_config(args.n),
+        "solver": {"linear": "GMRES(30), classical Gram-Schmidt with one reduction per iteration, left PC, rtol 1e-5",
+                   "preconditioner": "two-stage: AMG V(1,1) on the potential block + node-block Jacobi",
                    "matrix_format": "SELL-32 3x3 node blocks, FP64; the structurally zero block entry (1 of 9) is kept in the "
                                     "exported dolfin pattern but not streamed",
                    "parallelism": f"vertex partition x{world}" if world > 1 else "single GPU"},
@@ -284,9 +295,9 @@ def main():
     if not args.no_cpu_baseline and world == 1:
         try:
             from oracle import cpu_baseline
-            res = cpu_baseline.run(steps=1, warmup=0, full_n=args.n, sample_n=args.sample_n)
+            res = cpu_baseline.sample(full_n=args.n)
             line["cpu_baseline"] = {"value": res["value"], "unit": "steps/s", "cores": res["cores"], "kind": res["kind"],
-                                    "sample": res["sample"]}
+                                    "sample": res["sample"], "exponent": res["exponent"], "measured": res["measured"]}
         except Exception as exc:                                # the baseline must never sink the GPU number
             line["cpu_baseline"] = {"value": None, "unit": "steps/s", "cores": 0, "kind": "port", "sample": f"failed: {exc}"}
     print(json.dumps(line), flush=True)

@@ -1,68 +1,82 @@
 """CPU baseline for bench.py (oracle -- test infrastructure / reported baseline only, never the product path).
 
-The literal reference (FEniCS 2019.1.0 + PETSc under mpirun) cannot run in this image (no dolfin/PETSc/MPI,
-no network), so the reported CPU number is the oracle port timed on the box's host cores
-on a BOUNDED sample of the bench workload: the same streamer BDF2 step on a smaller n x n grid, scaled to the
-full mesh by the DOF ratio (assumes linear cost in DOF, which favours the CPU: Krylov/LU costs grow faster).
-Preference order: the compiled C/OpenMP restatement (oracle/csrc, kind "port", all cores) when it has been
-built, else the numpy/scipy oracle (kind "port", 1 core).
+The literal reference (FEniCS 2019.1.0 + PETSc under mpirun) cannot run in this image (no dolfin/PETSc/MPI, no network;
+SURVEY.md section 8c).  The reported CPU number is the compiled C++/OpenMP restatement of the same hot path
+(oracle/csrc/streamer_ref.cpp via oracle/streamer_c.py): owner-computes assembly and GMRES(30) + block-Jacobi/ILU(0) -- the
+reference test's KSP (fedm_streamer.py:32) with PETSc's parallel default PC -- on ALL host cores, one OpenMP thread per
+"rank".  It is parity-checked against the numpy oracle (tests/test_oracle_cport.py).
+
+Two entry points:
+  full(...)    bench.py --impl reference: the bench configuration ITSELF (n = 1825, 10.0 M DOF), timed per accepted BDF2
+               step; the start state is the oracle's (IC + sparse-LU initial Poisson solve, fedm_streamer.py:194-223)
+  sample(...)  the `cpu_baseline` object of the GPU line: a bounded sample (~10-30 s): one BDF2 step each on two smaller grids
+               of the same family, extrapolated to the bench mesh with the MEASURED cost exponent (not assumed linear)
 """
-import ctypes
+import math
 import os
 import time
-from pathlib import Path
 
 import numpy as np
 
-HERE = Path(__file__).resolve().parent
+
+def _initial_state(mesh):
+    from .streamer import StreamerProblem
+    return StreamerProblem(mesh).initial_state()
 
 
-def _c_port():
-    so = HERE / "csrc" / "libstreamer_ref.so"
-    if not so.exists():
-        return None
-    try:
-        return ctypes.CDLL(str(so))
-    except OSError:
-        return None
-
-
-def _replica(args):
-    """One independent copy of the sample workload (runs in its own process, numpy threads pinned to 1)."""
-    n, total, warmup = args
-    os.environ["OMP_NUM_THREADS"] = os.environ["OPENBLAS_NUM_THREADS"] = os.environ["MKL_NUM_THREADS"] = "1"
-    from .streamer import StreamerProblem, streamer_mesh
-    prob = StreamerProblem(streamer_mesh(n))
-    times = []
+def _time_steps(n, steps, warmup, threads, budget_s):
+    from . import streamer_c
+    from .streamer import streamer_mesh
     t0 = time.perf_counter()
-    prob.run(max_steps=total, callback=lambda step, t, x: times.append(time.perf_counter()))
-    per = np.diff([t0] + times)
-    # the first interval contains the initial Poisson solve + pattern set-up: excluded when there is a later step
-    used = per[max(warmup, 1 if len(per) > 1 else 0):] if len(per) > 1 else per
-    return float(np.mean(used)), len(used)
+    mesh = streamer_mesh(n)
+    x0 = _initial_state(mesh)
+    prob = streamer_c.StreamerC(mesh, threads)
+    setup_s = time.perf_counter() - t0
+    marks = []
+    t_start = time.perf_counter()
+
+    def on_step(k, t, x):
+        marks.append(time.perf_counter())
+        return not (k >= warmup + 1 and marks[-1] - t_start > budget_s)
+
+    _, rows, stats = prob.run(x0, max_steps=warmup + steps, on_step=on_step)
+    per = np.diff([t_start] + marks)
+    timed = per[warmup:] if len(per) > warmup else per[-1:]
+    out = {"s_per_step": float(np.mean(timed)), "timed_steps": int(len(timed)), "warmup_done": int(len(per) - len(timed)),
+           "cores": prob.threads, "setup_s": setup_s, "dof": 3 * mesh.num_vertices,
+           "newton_its_per_step": float(np.mean([s[0] for s in stats[-len(timed):]])),
+           "krylov_its_per_step": float(np.mean([s[1] for s in stats[-len(timed):]])), "phase_seconds_total": prob.timers()}
+    prob.close()
+    return out
 
 
-def run(steps=1, warmup=0, full_n=1825, sample_n=0, procs=0):
-    """CPU arm.  The oracle's sparse LU is single-threaded, so ALL host cores are used the way ``mpirun -np <cores>`` of
-    independent jobs would: one replica of the sample workload per core, throughput summed (no communication cost is
-    charged to the CPU side, which favours it)."""
+def full(steps=1, warmup=0, n=1825, threads=0, budget_s=200.0):
+    """The bench configuration itself on all host cores.  Warm-up is capped at one step and the run stops at the wall-clock
+    budget (one step at 10 M DOF takes minutes on a CPU): the number of steps actually timed is returned and printed."""
+    r = _time_steps(n, steps, min(warmup, 1), threads, budget_s)
+    r["value"] = 1.0 / r["s_per_step"]
+    r["kind"] = "port"
+    r["sample"] = (f"C++/OpenMP restatement (oracle/csrc/streamer_ref.cpp) on the bench mesh itself, n={n} ({r['dof']} DOF): "
+                   f"{r['cores']} threads = {r['cores']} 'ranks' (owner-computes assembly, GMRES(30) rtol 1e-5 + block-Jacobi/ILU(0) = the "
+                   f"reference test's KSP under mpirun); {r['timed_steps']} timed accepted BDF2 step(s) after {r['warmup_done']} warm-up "
+                   f"step(s) ({steps} requested; wall-clock budget {budget_s:.0f} s), {r['krylov_its_per_step']:.0f} Krylov and "
+                   f"{r['newton_its_per_step']:.1f} Newton iterations per step; set-up incl. the sparse-LU initial Poisson solve "
+                   f"{r['setup_s']:.0f} s (untimed); host has {os.cpu_count()} cores")
+    return r
+
+
+def sample(full_n=1825, sizes=(256, 512), threads=0):
+    """Bounded sample for the GPU line's `cpu_baseline`: one timed step (after one warm-up step) on each of two smaller grids;
+    the cost exponent p in t ~ DOF^p is MEASURED from the two and used to place the number on the bench mesh."""
+    rs = [_time_steps(n, 1, 1, threads, 1e9) for n in sizes]
     full_dof = 3 * (full_n + 1) ** 2
-    lib = _c_port()
-    if lib is not None:
-        from . import streamer_c
-        return streamer_c.timed_steps(lib, steps, warmup, full_n, sample_n or 512)
-    import multiprocessing as mp
-    n = sample_n or 96
-    total = max(1, steps) + warmup
-    cores = procs or max(1, min(os.cpu_count() or 1, 64))
-    if cores > 1:
-        with mp.get_context("spawn").Pool(cores) as pool:
-            res = pool.map(_replica, [(n, total, warmup)] * cores)
-    else:
-        res = [_replica((n, total, warmup))]
-    sps_sample = sum(1.0 / r[0] for r in res)                      # aggregate steps/s over the replicas
-    dof = 3 * (n + 1) ** 2
-    return {"value": sps_sample * dof / full_dof, "cores": cores, "kind": "port",
-            "sample": f"numpy/scipy oracle, {cores} independent replica(s) (one per host core), {res[0][1]} BDF2 step(s) each on a "
-                      f"{n}x{n} grid ({dof} DOF, exact sparse LU = the reference examples' 'mumps' mode), aggregate "
-                      f"throughput scaled to {full_dof} DOF by the DOF ratio; host has {os.cpu_count()} cores"}
+    p = math.log(rs[1]["s_per_step"] / rs[0]["s_per_step"]) / math.log(rs[1]["dof"] / rs[0]["dof"])
+    t_full = rs[1]["s_per_step"] * (full_dof / rs[1]["dof"]) ** p
+    return {"value": 1.0 / t_full, "cores": rs[1]["cores"], "kind": "port", "exponent": p,
+            "measured": [{"n": n, "dof": r["dof"], "s_per_step": r["s_per_step"], "krylov_its_per_step": r["krylov_its_per_step"]}
+                         for n, r in zip(sizes, rs)],
+            "sample": f"C++/OpenMP restatement (oracle/csrc/streamer_ref.cpp), {rs[1]['cores']} threads, GMRES(30) rtol 1e-5 + "
+                      f"block-Jacobi/ILU(0): one accepted BDF2 step (after one warm-up step) on the n={sizes[0]} and n={sizes[1]} grids "
+                      f"({rs[0]['s_per_step']:.2f} s, {rs[1]['s_per_step']:.2f} s; {rs[0]['krylov_its_per_step']:.0f} / "
+                      f"{rs[1]['krylov_its_per_step']:.0f} Krylov iterations), extrapolated to {full_dof} DOF with the measured exponent "
+                      f"t ~ DOF^{p:.2f}; `bench.py --impl reference` times the full mesh itself; host has {os.cpu_count()} cores"}
