@@ -113,16 +113,17 @@ __global__ void __launch_bounds__(128) dinv_extract_kernel(SellView S, const dou
     const int64_t s = row / FEDMX_SLICE;
     const int lane = int(row % FEDMX_SLICE);
     const double *d = dinv + s * FEDMX_SLICE * NB + lane;
+    const int64_t node = S.row_node[row];
     double in[NEQ];
 #pragma unroll
-    for (int l = 0; l < NEQ; ++l) in[l] = r[int64_t(NEQ) * row + l];
+    for (int l = 0; l < NEQ; ++l) in[l] = r[int64_t(NEQ) * node + l];
 #pragma unroll
     for (int i = 0; i < NEQ; ++i) {
         double acc = 0.0;
 #pragma unroll
         for (int l = 0; l < NEQ; ++l) acc = fma(d[(i * NEQ + l) * FEDMX_SLICE], in[l], acc);
-        z[int64_t(NEQ) * row + i] = acc;
-        if (i == comp) rhs_c[row] = in[i];
+        z[int64_t(NEQ) * node + i] = acc;
+        if (i == comp) rhs_c[node] = in[i];
     }
 }
 
@@ -616,7 +617,8 @@ extern "C" int fedmx_matrix_get_component(fedmx_ctx *ctx, int i, int j, double *
                                        cudaMemcpyDeviceToHost));
     const auto &rp = ctx->h_rowptr;
     for (int64_t r = 0; r < ctx->n_owned; ++r) {
-        const int64_t s = r / FEDMX_SLICE, l = r % FEDMX_SLICE;
+        const int64_t sr = ctx->h_node_row[r];
+        const int64_t s = sr / FEDMX_SLICE, l = sr % FEDMX_SLICE;
         for (int32_t q = rp[r]; q < rp[r + 1]; ++q)
             h_values[q] = plane[int64_t(ctx->h_slice_ptr[s]) + int64_t(q - rp[r]) * FEDMX_SLICE + l];
     }

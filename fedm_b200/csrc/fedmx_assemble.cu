@@ -16,6 +16,7 @@
 #include "quadrature_tables.h"
 
 #include "row_kernel.cuh"
+#include "tiled_kernel.cuh"
 
 namespace {
 
@@ -36,6 +37,215 @@ struct StreamerModel {
     static constexpr int NF = 2;
     static constexpr int NC = 2;      // nodal c_s = exp(u_s/6): e^{u(q)} at the 3-point rule is a product of them
     typedef Vtx<3, 2, 2> V;
+
+    // ---- tiled (cell-batch) kernel, tiled_kernel.cuh ---------------------------------------------------------------
+    // staged vertex fields: r, z, u_i, u_e, Phi, hist_i, hist_e, c_i = exp(u_i/6), c_e = exp(u_e/6)
+    // cell record (residual): P.g_k [0..2], G.g_k [3..5], S [6], w0 [7];  Jacobian adds Q.g_k [8..10], g_i.g_j [11..16]
+    // (0,0 1,1 2,2 0,1 0,2 1,2), 1/|E| [17], mu [18], D [19], dS/d|E| [20]      (P = -D grad u_e + mu grad Phi, Q = dP/d|E|)
+    static constexpr bool TILED = true;
+    static constexpr int NVF = 9, NREC_RES = 8, NREC_JAC = 21, TILED_MINB = 3;
+
+    struct VtxRaw { double r, z, u0, u1, u2, h0, h1; };
+    static __device__ __forceinline__ VtxRaw stage_load(const AsmArgs &A, int32_t node) {
+        VtxRaw v;
+        const double2 c = *reinterpret_cast<const double2 *>(A.coords + 2 * int64_t(node));
+        v.u0 = __ldg(A.x + 3 * int64_t(node)); v.u1 = __ldg(A.x + 3 * int64_t(node) + 1); v.u2 = __ldg(A.x + 3 * int64_t(node) + 2);
+        const double2 h = *reinterpret_cast<const double2 *>(A.fields + 2 * int64_t(node));
+        v.r = c.x; v.z = c.y; v.h0 = h.x; v.h1 = h.y;
+        return v;
+    }
+    static __device__ __forceinline__ void stage_store(const TileSmem &sm, int i, const VtxRaw &v) {
+        sm.v(0, i) = v.r; sm.v(1, i) = v.z;
+        sm.v(2, i) = v.u0; sm.v(3, i) = v.u1; sm.v(4, i) = v.u2;
+        sm.v(5, i) = v.h0; sm.v(6, i) = v.h1;
+        sm.v(7, i) = exp(v.u0 * (1.0 / 6.0));
+        sm.v(8, i) = exp(v.u1 * (1.0 / 6.0));
+    }
+    static __device__ __forceinline__ void stage(const AsmArgs &A, int32_t node, const TileSmem &sm, int i) {
+        stage_store(sm, i, stage_load(A, node));
+    }
+
+    template <bool JAC>
+    static __device__ __forceinline__ void cell(const ModelParams &mp, const TileSmem &sm, int l0, int l1, int l2, int c) {
+        const double r0 = sm.v(0, l0), z0 = sm.v(1, l0), r1 = sm.v(0, l1), z1 = sm.v(1, l1), r2 = sm.v(0, l2), z2 = sm.v(1, l2);
+        const double e1r = r1 - r0, e1z = z1 - z0, e2r = r2 - r0, e2z = z2 - z0;
+        const double det = e1r * e2z - e1z * e2r;
+        const double inv = 1.0 / det;
+        double gr[3], gz[3];
+        gr[1] = e2z * inv; gz[1] = -e2r * inv;
+        gr[2] = -e1z * inv; gz[2] = e1r * inv;
+        gr[0] = -gr[1] - gr[2]; gz[0] = -gz[1] - gz[2];
+        const double ue0 = sm.v(3, l0), ue1 = sm.v(3, l1), ue2 = sm.v(3, l2);
+        const double ph0 = sm.v(4, l0), ph1 = sm.v(4, l1), ph2 = sm.v(4, l2);
+        const double Gr = ph0 * gr[0] + ph1 * gr[1] + ph2 * gr[2], Gz = ph0 * gz[0] + ph1 * gz[1] + ph2 * gz[2];
+        const double Hr = ue0 * gr[0] + ue1 * gr[1] + ue2 * gr[2], Hz = ue0 * gz[0] + ue1 * gz[1] + ue2 * gz[2];
+        const double Em = sqrt(Gr * Gr + Gz * Gz);
+        const double iEm = 1.0 / Em;
+        const double lnE = log(Em);
+        const double mu = mp.p[0] * exp(mp.p[1] * lnE);
+        const double D = mp.p[2] * exp(mp.p[3] * lnE);
+        const double iE3 = iEm * iEm * iEm;
+        const double ex = exp(-mp.p[6] * iEm);
+        const double pre = mp.p[4] + mp.p[5] * iE3;
+        const double alpha = pre * ex - mp.p[7];
+        const double Pr = -D * Hr + mu * Gr, Pz = -D * Hz + mu * Gz;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            sm.r(k, c) = Pr * gr[k] + Pz * gz[k];
+            sm.r(3 + k, c) = Gr * gr[k] + Gz * gz[k];
+        }
+        sm.r(6, c) = alpha * mu * Em;
+        sm.r(7, c) = fabs(det) * (1.0 / 6.0) * kTwoPi;
+        if (JAC) {
+            const double dmu = mp.p[1] * mu * iEm;
+            const double dD = mp.p[3] * D * iEm;
+            const double dalpha = (-3.0 * mp.p[5] * iE3 * iEm + pre * mp.p[6] * iEm * iEm) * ex;
+            const double Qr = -dD * Hr + dmu * Gr, Qz = -dD * Hz + dmu * Gz;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                sm.r(8 + k, c) = Qr * gr[k] + Qz * gz[k];
+                sm.r(11 + k, c) = gr[k] * gr[k] + gz[k] * gz[k];
+            }
+            sm.r(14, c) = gr[0] * gr[1] + gz[0] * gz[1];
+            sm.r(15, c) = gr[0] * gr[2] + gz[0] * gz[2];
+            sm.r(16, c) = gr[1] * gr[2] + gz[1] * gz[2];
+            sm.r(17, c) = iEm;
+            sm.r(18, c) = mu;
+            sm.r(19, c) = D;
+            sm.r(20, c) = dalpha * mu * Em + alpha * dmu * Em + alpha * mu;
+        }
+    }
+
+    static __device__ __forceinline__ void load_staged(const TileSmem &sm, int l, V &v) {
+        v.id = l;
+        v.r = sm.v(0, l); v.z = sm.v(1, l);
+        v.u[0] = sm.v(2, l); v.u[1] = sm.v(3, l); v.u[2] = sm.v(4, l);
+        v.f[0] = sm.v(5, l); v.f[1] = sm.v(6, l);
+        v.c[0] = sm.v(7, l); v.c[1] = sm.v(8, l);
+    }
+
+    struct MiniParams { double p[10], dt, dt_old; };     // what row<JAC>() reads, passed by value to the boundary-row path
+    static __device__ __forceinline__ MiniParams compact(const ModelParams &mp) {
+        MiniParams q;
+#pragma unroll
+        for (int i = 0; i < 10; ++i) q.p[i] = mp.p[i];
+        q.dt = mp.dt;
+        q.dt_old = mp.dt_old;
+        return q;
+    }
+    static __device__ __forceinline__ ModelParams expand(const MiniParams &q) {
+        ModelParams mp;
+#pragma unroll
+        for (int i = 0; i < 10; ++i) mp.p[i] = q.p[i];
+        mp.dt = q.dt;
+        mp.dt_old = q.dt_old;
+        return mp;
+    }
+
+    // per-row registers of the tiled walk: the row's own vertex and the "next" vertex of the previous cell (= the "previous"
+    // vertex of the current one: consecutive cells of a fan share an edge), fields r, u_i, u_e, hist_i, hist_e, c_i, c_e
+    struct RowState { double a[7], n[7]; };
+    static __device__ __forceinline__ void load7(const TileSmem &sm, int l, double *d) {
+        d[0] = sm.v(0, l); d[1] = sm.v(2, l); d[2] = sm.v(3, l); d[3] = sm.v(5, l); d[4] = sm.v(6, l); d[5] = sm.v(7, l); d[6] = sm.v(8, l);
+    }
+    static __device__ __forceinline__ void row_begin(const ModelParams &, const TileSmem &sm, int la, RowState &st) {
+        load7(sm, la, st.a);
+#pragma unroll
+        for (int k = 0; k < 7; ++k) st.n[k] = 0.0;
+    }
+
+    static __device__ __forceinline__ int sym6(int i, int j) { return i == j ? i : i + j + 2; }
+
+    // Row `a` of the element tensor from the staged vertices (a, p, n) and the cell record.  3-point rule: the point
+    // belonging to vertex q has lambda_q = 2/3 and 1/6 elsewhere, i.e. f(q) = (f_a + f_p + f_n)/6 + f_q/2.
+    template <bool JAC>
+    static __device__ __forceinline__ void row_rec(const ModelParams &mp, const TileSmem &sm, RowState &st, int c, int ka, int kp, int kn,
+                                                   int lp, int ln, bool first, RowOut<3> &o) {
+        const double sixth = 1.0 / 6.0;
+        double pv[7];
+        if (first) load7(sm, lp, pv);                    // a new fan starts here (first cell, or a non-manifold vertex)
+        else {
+#pragma unroll
+            for (int k = 0; k < 7; ++k) pv[k] = st.n[k];
+        }
+        load7(sm, ln, st.n);
+        double r[3], ui[3], ue[3], hi[3], he[3], ci[3], ce[3];
+        r[0] = st.a[0]; ui[0] = st.a[1]; ue[0] = st.a[2]; hi[0] = st.a[3]; he[0] = st.a[4]; ci[0] = st.a[5]; ce[0] = st.a[6];
+        r[1] = pv[0]; ui[1] = pv[1]; ue[1] = pv[2]; hi[1] = pv[3]; he[1] = pv[4]; ci[1] = pv[5]; ce[1] = pv[6];
+        r[2] = st.n[0]; ui[2] = st.n[1]; ue[2] = st.n[2]; hi[2] = st.n[3]; he[2] = st.n[4]; ci[2] = st.n[5]; ce[2] = st.n[6];
+        const double Pga = sm.r(ka, c), Gga = sm.r(3 + ka, c), S = sm.r(6, c), w0 = sm.r(7, c);
+        const double kappa = mp.p[8];
+        const double tr = mp.dt / mp.dt_old;
+        const double ct = (1.0 + 2.0 * tr) / ((1.0 + tr) * mp.dt);
+        const double sr = (r[0] + r[1] + r[2]) * sixth, sui = (ui[0] + ui[1] + ui[2]) * sixth, sue = (ue[0] + ue[1] + ue[2]) * sixth;
+        const double shi = (hi[0] + hi[1] + hi[2]) * sixth, she = (he[0] + he[1] + he[2]) * sixth;
+        const double Ti = ci[0] * ci[1] * ci[2], Te = ce[0] * ce[1] * ce[2];
+        double X0[3], X1[3], X2[3], Wne[3], Wni[3], bic[3], bec[3];
+        double Wsum = 0.0, Mne = 0.0;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const double W = w0 * fma(0.5, r[q], sr);
+            const double bi = fma(ct, fma(0.5, ui[q], sui), fma(0.5, hi[q], shi));
+            const double be = fma(ct, fma(0.5, ue[q], sue), fma(0.5, he[q], she));
+            Wni[q] = W * (Ti * (ci[q] * ci[q] * ci[q]));
+            Wne[q] = W * (Te * (ce[q] * ce[q] * ce[q]));
+            X0[q] = Wni[q] * bi - S * Wne[q];
+            X1[q] = Wne[q] * be - S * Wne[q];
+            X2[q] = Wni[q] - Wne[q];
+            bic[q] = bi + ct;
+            bec[q] = be + ct;
+            Wsum += W;
+            Mne += Wne[q];
+        }
+        o.R[0] = fma(0.5, X0[0], (X0[0] + X0[1] + X0[2]) * sixth);
+        o.R[1] = fma(0.5, X1[0], (X1[0] + X1[1] + X1[2]) * sixth) - Mne * Pga;
+        o.R[2] = Wsum * Gga - kappa * fma(0.5, X2[0], (X2[0] + X2[1] + X2[2]) * sixth);
+        if (JAC) {
+            const double Qga = sm.r(8 + ka, c), iEm = sm.r(17, c), mu = sm.r(18, c), D = sm.r(19, c), dS = sm.r(20, c);
+            // moments sum_q T_q lambda_a(q) lambda_b(q):  t'_q = T_q lambda_a(q),  M_b = (t'_a + t'_p + t'_n)/6 + t'_b/2
+            const double la6[3] = {2.0 / 3.0, sixth, sixth};
+            double Mii[3], Mee[3], Mne2[3], Mni2[3], Nb[3];
+            {
+                double t0[3], t1[3], t2[3], t3[3];
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    t0[q] = Wni[q] * bic[q] * la6[q];
+                    t1[q] = (Wne[q] * bec[q] - S * Wne[q]) * la6[q];
+                    t2[q] = Wne[q] * la6[q];
+                    t3[q] = Wni[q] * la6[q];
+                }
+                const double s0 = (t0[0] + t0[1] + t0[2]) * sixth, s1 = (t1[0] + t1[1] + t1[2]) * sixth;
+                const double s2 = (t2[0] + t2[1] + t2[2]) * sixth, s3 = (t3[0] + t3[1] + t3[2]) * sixth;
+                const double mne6 = Mne * sixth;
+#pragma unroll
+                for (int b = 0; b < 3; ++b) {
+                    Mii[b] = fma(0.5, t0[b], s0);
+                    Mee[b] = fma(0.5, t1[b], s1);
+                    Mne2[b] = fma(0.5, t2[b], s2);
+                    Mni2[b] = fma(0.5, t3[b], s3);
+                    Nb[b] = fma(0.5, Wne[b], mne6);
+                }
+            }
+            const double Mne0 = Nb[0];
+            const int kv[3] = {ka, kp, kn};
+#pragma unroll
+            for (int b = 0; b < 3; ++b) {
+                double *J = o.J[b];
+                const double Ghb = sm.r(3 + kv[b], c) * iEm;           // d|E| / dPhi_b
+                const double gbga = sm.r(11 + sym6(ka, kv[b]), c);
+                const double j2 = -dS * Ghb * Mne0;
+                J[0] = Mii[b];
+                J[1] = -S * Mne2[b];
+                J[2] = j2;
+                J[3] = 0.0;
+                J[4] = Mee[b] + Mne * D * gbga - Nb[b] * Pga;
+                J[5] = j2 - Mne * (Qga * Ghb + mu * gbga);
+                J[6] = -kappa * Mni2[b];
+                J[7] = kappa * Mne2[b];
+                J[8] = Wsum * gbga;
+            }
+        }
+    }
 
     // facet (a,b): b is local vertex LB (1 = p, 2 = n), c the opposite vertex
     template <bool JAC, int LB>
@@ -190,6 +400,7 @@ struct StreamerModel {
 // initial potential, fedm_streamer.py:210-223.  params: [0] = kappa = e/eps0.  Degree-2 quadrature.
 // =====================================================================================================
 struct PoissonModel {
+    static constexpr bool TILED = false;
     static constexpr int MINB = 2, MINB_RES = 2;
     static constexpr unsigned ZERO_MASK = 0;
     static constexpr int NC = 0;
@@ -238,6 +449,7 @@ struct PoissonModel {
 // params: [0]=D [1]=w_z [2]=alpha ;  mp.t = time of the new level ;  fields: [0]=BDF2 history
 // =====================================================================================================
 struct TofModel {
+    static constexpr bool TILED = false;
     static constexpr int MINB = 2, MINB_RES = 2;
     static constexpr unsigned ZERO_MASK = 0;
     static constexpr int NC = 0;
@@ -309,6 +521,7 @@ struct TofModel {
 // params: [0] = mode (0: g = exp(field0), 1: g = scale*|grad field0|)  [1] = scale ;  fields: [0] = P1 input
 // =====================================================================================================
 struct ProjectionModel {
+    static constexpr bool TILED = false;
     static constexpr int MINB = 2, MINB_RES = 2;
     static constexpr unsigned ZERO_MASK = 0;
     static constexpr int NC = 0;
@@ -370,6 +583,27 @@ __global__ void nodal_exp6_kernel(const double *__restrict__ x, int n_eq, int nc
 template <class Model>
 int launch_assembly(fedmx_ctx *ctx, const double *d_x, double *d_b, bool jac) {
     AsmArgs A;
+    // cell-batch (tiled) kernel for the models that provide cell records; FEDMX_ASM_TILED=0 forces the generic row kernel
+    static const bool env_tiled = !(getenv("FEDMX_ASM_TILED") && atoi(getenv("FEDMX_ASM_TILED")) == 0);
+    if constexpr (Model::TILED) {
+        if (env_tiled && ctx->tiles.n_tiles > 0) {
+            A.nodal = nullptr;
+            for (int k = 0; k < FEDMX_MAX_REFS; ++k) A.refs[k] = ctx->plugin_refs[k];
+            A.S = ctx->sell;
+            A.coords = ctx->d_coords;
+            A.x = d_x;
+            A.fields = ctx->d_fields;
+            A.val = jac ? ctx->d_val : nullptr;
+            A.res = d_b;
+            A.mp = ctx->mp;
+            ProfScope prof(ctx, jac ? FEDMX_PROF_ASM_JAC : FEDMX_PROF_ASM_RES);
+            if (launch_tiled<Model>(A, ctx->tiles, jac, ctx->stream)) {
+                ctx->launches++;
+                FEDMX_CHECK_CUDA(ctx, cudaGetLastError());
+                return FEDMX_OK;
+            }
+        }
+    }
     if (Model::NC > 0) {
         if (!ctx->d_nodal) {
             int rc = fedmx_dev_alloc(ctx, &ctx->d_nodal, size_t(ctx->n_vertices) * Model::NC);

@@ -93,7 +93,11 @@ extern "C" int fedmx_profile_get(fedmx_ctx *ctx, int kind, int64_t *count, doubl
 
 // Step-size controllers: plain libm pow() so that the dt sequence is bit-identical to the reference's
 // Python floats (reference: fedm/functions.py:915-951; pinned by the golden relative-error logs).
-static double clampd(double dt, double dt_min, double dt_max) { return fmax(fmin(dt, dt_max), dt_min); }
+// Python's max(min(dt, dt_max), dt_min): a NaN step size propagates (fmin/fmax would silently turn it into dt_max)
+static double clampd(double dt, double dt_min, double dt_max) {
+    const double lo = (dt_max < dt) ? dt_max : dt;
+    return (dt_min > lo) ? dt_min : lo;
+}
 
 extern "C" double fedmx_pid_step(double dt, const double err[3], double tol, double dt_min, double dt_max) {
     dt *= pow(err[1] / err[0], 0.075) * pow(tol / err[0], 0.175) * pow(err[1] * err[1] / (err[0] * err[2]), 0.01);

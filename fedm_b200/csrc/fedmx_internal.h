@@ -39,7 +39,29 @@ struct SellView {
     const int32_t *inc_vp;      // neighbour vertex shared with the previous cell of the fan
     const int32_t *inc_vn;      // neighbour vertex shared with the next cell of the fan
     const uint32_t *inc_pack;   // see PACK_* below
-    const uint32_t *row_pack;   // [n_slices*32]: n_inc | diag_slot<<8 | bc_value_index+1 <<16
+    const uint32_t *row_pack;   // [n_slices*32]: n_inc | diag_slot<<8 | bc_value_index+1 <<16 | (row touches a marked exterior facet) <<31
+    // Storage row r (slice r/32, lane r%32) holds mesh node row_node[r].  The rows are ordered in spatially compact tiles
+    // of FEDMX_TILE consecutive rows (recursive coordinate bisection, fedmx_topology.cu), so that one CTA of the tiled
+    // assembly kernel -- and one L1 -- sees a 2-D patch of the mesh; vectors stay in the caller's node order.
+    const int32_t *row_node;    // [n_slices*32], padding rows: -1
+};
+
+#define FEDMX_TILE 128
+
+// Cell batches of the tiled assembly kernel: tile t = storage rows [128 t, 128 t + 128).  Its vertex set is the tile's own
+// nodes (local index = row - 128 t) followed by `n_halo` ring vertices; its cells are all cells incident to its rows.
+struct TileInfo {
+    int32_t cell_off, n_cells;   // into cellv
+    int32_t halo_off, n_halo;    // into halo
+};
+struct TileView {
+    int64_t n_tiles = 0;
+    int max_cells = 0, max_vtx = 0;
+    const TileInfo *info = nullptr;
+    const int32_t *halo = nullptr;          // node ids of the ring vertices
+    const unsigned long long *cellv = nullptr;   // per cell: local vertex indices v0 | v1<<16 | v2<<32
+    const uint32_t *inc_cell = nullptr;     // fan layout (like inc_pack): local cell | ka<<12 | kp<<14  (ka/kp: position of the row's
+                                            // node / of the fan's "previous" vertex inside the cell)
 };
 
 // inc_pack bit layout
@@ -116,6 +138,8 @@ struct fedmx_ctx {
     int64_t n_owned = 0;         // owned vertices are numbered first
     double *d_coords = nullptr;  // [n_vertices][2]
     SellView sell{};
+    TileView tiles{};
+    std::vector<int32_t> h_row_node, h_node_row;   // storage row <-> owned node
     std::vector<void *> owned_device;   // everything cudaMalloc'ed by set-up calls
     std::vector<void *> amg_device;     // multigrid hierarchy: released by fedmx_amg_reset (re-running set-up must not leak)
     std::vector<void *> *alloc_pool = nullptr;   // where fedmx_dev_alloc records (default: owned_device)

@@ -70,10 +70,11 @@ __global__ void __launch_bounds__(128, 16) spmv_kernel(SellView S, const double 
                 if (!((zmask >> (i * NEQ + l)) & 1u)) acc[i] = fma(__ldcs(v + (i * NEQ + l) * FEDMX_SLICE), xc[l], acc[i]);
     }
     if (row >= S.n_rows) return;
+    const int64_t node = S.row_node[row];                // vectors live in node order, the matrix in tiled storage order
     if (EXTRACT) {
 #pragma unroll
         for (int i = 0; i < NEQ; ++i)
-            if (i == comp) rhs_c[row] = acc[i];
+            if (i == comp) rhs_c[node] = acc[i];
     }
     if (PRECOND) {
         const double *d = dinv + s * FEDMX_SLICE * NB + lane;
@@ -85,10 +86,10 @@ __global__ void __launch_bounds__(128, 16) spmv_kernel(SellView S, const double 
             for (int l = 0; l < NEQ; ++l) z[i] = fma(d[(i * NEQ + l) * FEDMX_SLICE], acc[l], z[i]);
         }
 #pragma unroll
-        for (int i = 0; i < NEQ; ++i) y[int64_t(NEQ) * row + i] = z[i];
+        for (int i = 0; i < NEQ; ++i) y[int64_t(NEQ) * node + i] = z[i];
     } else {
 #pragma unroll
-        for (int i = 0; i < NEQ; ++i) y[int64_t(NEQ) * row + i] = acc[i];
+        for (int i = 0; i < NEQ; ++i) y[int64_t(NEQ) * node + i] = acc[i];
     }
 }
 
@@ -151,15 +152,16 @@ __global__ void apply_dinv_kernel(SellView S, const double *__restrict__ dinv, c
     const int64_t s = row / FEDMX_SLICE;
     const int lane = int(row % FEDMX_SLICE);
     const double *d = dinv + s * FEDMX_SLICE * NB + lane;
+    const int64_t node = S.row_node[row];
     double in[NEQ];
 #pragma unroll
-    for (int l = 0; l < NEQ; ++l) in[l] = r[int64_t(NEQ) * row + l];
+    for (int l = 0; l < NEQ; ++l) in[l] = r[int64_t(NEQ) * node + l];
 #pragma unroll
     for (int i = 0; i < NEQ; ++i) {
         double acc = 0.0;
 #pragma unroll
         for (int l = 0; l < NEQ; ++l) acc = fma(d[(i * NEQ + l) * FEDMX_SLICE], in[l], acc);
-        z[int64_t(NEQ) * row + i] = acc;
+        z[int64_t(NEQ) * node + i] = acc;
     }
 }
 

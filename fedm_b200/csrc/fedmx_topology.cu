@@ -12,6 +12,8 @@
 #include <algorithm>
 #include <cstring>
 #include <numeric>
+#include <stdlib.h>
+#include <string>
 
 #include "fedmx_internal.h"
 
@@ -20,7 +22,50 @@ namespace {
 struct Inc {
     int32_t vp, vn;
     uint32_t pack;
+    int32_t cell;
 };
+
+// Recursive coordinate bisection of the owned nodes into tiles of FEDMX_TILE nodes (the last one may be smaller): every split
+// puts a whole number of tiles on the left and cuts the longer side, measured in GRID units (dense ranks of the coordinates,
+// so that graded tensor-product meshes tile like uniform ones).  order[] is permuted in place.
+struct Rcb {
+    const std::vector<double> &ux, &uy;
+    std::vector<int32_t> &order;
+    void split(int64_t lo, int64_t hi) {
+        const int64_t n = hi - lo;
+        if (n <= FEDMX_TILE) return;
+        const int64_t tiles = (n + FEDMX_TILE - 1) / FEDMX_TILE;
+        const int64_t left = (tiles / 2) * FEDMX_TILE;
+        double x0 = 1e300, x1 = -1e300, y0 = 1e300, y1 = -1e300;
+        for (int64_t i = lo; i < hi; ++i) {
+            const int32_t v = order[i];
+            x0 = std::min(x0, ux[v]); x1 = std::max(x1, ux[v]);
+            y0 = std::min(y0, uy[v]); y1 = std::max(y1, uy[v]);
+        }
+        const bool cut_x = (x1 - x0) > (y1 - y0);
+        auto less = [&](int32_t a, int32_t b) {
+            const double ka = cut_x ? ux[a] : uy[a], kb = cut_x ? ux[b] : uy[b];
+            if (ka != kb) return ka < kb;
+            const double la = cut_x ? uy[a] : ux[a], lb = cut_x ? uy[b] : ux[b];
+            if (la != lb) return la < lb;
+            return a < b;
+        };
+        std::nth_element(order.begin() + lo, order.begin() + lo + left, order.begin() + hi, less);
+        split(lo, lo + left);
+        split(lo + left, hi);
+    }
+};
+
+std::vector<double> dense_rank(const double *coords, int comp, int64_t n) {
+    std::vector<double> vals(n);
+    for (int64_t i = 0; i < n; ++i) vals[i] = coords[2 * i + comp];
+    std::vector<double> uniq(vals);
+    std::sort(uniq.begin(), uniq.end());
+    uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+    std::vector<double> r(n);
+    for (int64_t i = 0; i < n; ++i) r[i] = double(std::lower_bound(uniq.begin(), uniq.end(), vals[i]) - uniq.begin());
+    return r;
+}
 
 inline int find_slot(const std::vector<int32_t> &colidx, int32_t lo, int32_t hi, int32_t col) {
     const int32_t *b = colidx.data() + lo, *e = colidx.data() + hi;
@@ -99,13 +144,32 @@ extern "C" int fedmx_mesh_set(fedmx_ctx *ctx, int n_eq, int64_t n_vertices, cons
         return (it != fkeys.end() && it->first == a * NV + b) ? uint32_t(it->second) : 0u;
     };
 
-    // ---- SELL-32 slicing of matrix slots
+    // ---- storage order of the rows: spatially compact tiles of FEDMX_TILE nodes, ascending node index inside a tile
     const int64_t n_slices = (NO + FEDMX_SLICE - 1) / FEDMX_SLICE;
+    std::vector<int32_t> &row_node = ctx->h_row_node, &node_row = ctx->h_node_row;
+    row_node.assign(n_slices * FEDMX_SLICE, -1);
+    node_row.assign(NO, -1);
+    {
+        std::vector<int32_t> order(NO);
+        std::iota(order.begin(), order.end(), 0);
+        static const bool tiled_rows = !(getenv("FEDMX_ROW_ORDER") && std::string(getenv("FEDMX_ROW_ORDER")) == "natural");
+        if (tiled_rows && NO > FEDMX_TILE) {
+            const std::vector<double> ux = dense_rank(h_coords, 0, NO), uy = dense_rank(h_coords, 1, NO);
+            Rcb rcb{ux, uy, order};
+            rcb.split(0, NO);
+            for (int64_t t = 0; t * FEDMX_TILE < NO; ++t)
+                std::sort(order.begin() + t * FEDMX_TILE, order.begin() + std::min<int64_t>(NO, (t + 1) * FEDMX_TILE));
+        }
+        for (int64_t r = 0; r < NO; ++r) { row_node[r] = order[r]; node_row[order[r]] = int32_t(r); }
+    }
+    auto rlen = [&](int64_t r) { const int32_t v = row_node[r]; return rowptr[v + 1] - rowptr[v]; };
+
+    // ---- SELL-32 slicing of matrix slots
     std::vector<int32_t> slice_ptr(n_slices + 1, 0), slice_width(n_slices, 0);
     for (int64_t s = 0; s < n_slices; ++s) {
         int w = 0;
         for (int64_t r = s * FEDMX_SLICE; r < std::min<int64_t>(NO, (s + 1) * FEDMX_SLICE); ++r)
-            w = std::max(w, rowptr[r + 1] - rowptr[r]);
+            w = std::max(w, rlen(r));
         slice_width[s] = w;
         int64_t next = int64_t(slice_ptr[s]) + int64_t(w) * FEDMX_SLICE;
         FEDMX_REQUIRE(ctx, next * n_eq * n_eq < (int64_t(1) << 31) * 4, "fedmx_mesh_set: matrix too large for this rank");
@@ -120,8 +184,8 @@ extern "C" int fedmx_mesh_set(fedmx_ctx *ctx, int n_eq, int64_t n_vertices, cons
             for (int k = 0; k < slice_width[s]; ++k) {
                 int64_t slot = int64_t(slice_ptr[s]) + int64_t(k) * FEDMX_SLICE + l;
                 int32_t c;
-                if (r < NO && k < rowptr[r + 1] - rowptr[r]) c = colidx[rowptr[r] + k];
-                else c = int32_t(r < NO ? r : 0);
+                if (r < NO && k < rlen(r)) c = colidx[rowptr[row_node[r]] + k];
+                else c = int32_t(r < NO ? row_node[r] : 0);
                 col[slot] = c;
             }
         }
@@ -180,7 +244,7 @@ extern "C" int fedmx_mesh_set(fedmx_ctx *ctx, int n_eq, int64_t n_vertices, cons
                     FEDMX_REQUIRE(ctx, sp >= 0 && sn >= 0, "fedmx_mesh_set: internal pattern error");
                     uint32_t pack = uint32_t(sp) | (uint32_t(sn) << 8) | (facet_marker(v, p) << 16) |
                                     (facet_marker(v, n) << 20);
-                    fan.push_back({p, n, pack});
+                    fan.push_back({p, n, pack, loc[cur].cell});
                     int nxt = next_cell(n, cur);
                     if (nxt < 0) {
                         // closed fans end where they started; otherwise this is an open end
@@ -195,27 +259,89 @@ extern "C" int fedmx_mesh_set(fedmx_ctx *ctx, int n_eq, int64_t n_vertices, cons
                 if (closed) { fan[first_idx].pack |= (1u << 26); fan.back().pack |= (1u << 26); }
             }
             int diag = find_slot(colidx, lo, hi, int32_t(v));
-            row_pack[v] = uint32_t(nloc) | (uint32_t(diag) << 8);
+            uint32_t marked = 0;
+            for (const Inc &in : fan) marked |= (in.pack >> 16) & 0xffu;
+            row_pack[node_row[v]] = uint32_t(nloc) | (uint32_t(diag) << 8) | (marked ? (1u << 31) : 0u);
         }
     }
     std::vector<int32_t> inc_ptr(n_slices + 1, 0), inc_width(n_slices, 0);
     for (int64_t s = 0; s < n_slices; ++s) {
         int w = 0;
         for (int64_t r = s * FEDMX_SLICE; r < std::min<int64_t>(NO, (s + 1) * FEDMX_SLICE); ++r)
-            w = std::max<int>(w, int(fans[r].size()));
+            w = std::max<int>(w, int(fans[row_node[r]].size()));
         inc_width[s] = w;
         inc_ptr[s + 1] = inc_ptr[s] + w * FEDMX_SLICE;
     }
     const int64_t n_inc = inc_ptr[n_slices];
     std::vector<int32_t> inc_vp(n_inc, 0), inc_vn(n_inc, 0);
-    std::vector<uint32_t> inc_pack(n_inc, 0);
+    std::vector<uint32_t> inc_pack(n_inc, 0), inc_cell(n_inc, 0);
     for (int64_t r = 0; r < NO; ++r) {
         int64_t s = r / FEDMX_SLICE, l = r % FEDMX_SLICE;
-        for (size_t m = 0; m < fans[r].size(); ++m) {
+        const std::vector<Inc> &fan = fans[row_node[r]];
+        for (size_t m = 0; m < fan.size(); ++m) {
             int64_t e = int64_t(inc_ptr[s]) + int64_t(m) * FEDMX_SLICE + l;
-            inc_vp[e] = fans[r][m].vp;
-            inc_vn[e] = fans[r][m].vn;
-            inc_pack[e] = fans[r][m].pack;
+            inc_vp[e] = fan[m].vp;
+            inc_vn[e] = fan[m].vn;
+            inc_pack[e] = fan[m].pack;
+        }
+    }
+
+    // ---- cell batches of the tiled assembly kernel: per tile the cells incident to its rows (numbered in the order the
+    // row threads first meet them: fan position major, lane minor, so that the lanes of a warp touch consecutive records),
+    // the ring of vertices outside the tile, and per fan entry (local cell, position of the row's node, position of vp)
+    const int64_t n_tiles = (NO + FEDMX_TILE - 1) / FEDMX_TILE;
+    std::vector<TileInfo> tinfo(n_tiles);
+    std::vector<int32_t> thalo;
+    std::vector<unsigned long long> tcellv;
+    int max_cells = 0, max_vtx = 0;
+    bool tiles_ok = true;
+    {
+        std::vector<int32_t> cell_loc(n_cells, -1), vtx_loc(NV, -1), touched_c, touched_v;
+        for (int64_t t = 0; t < n_tiles; ++t) {
+            const int64_t r0 = t * FEDMX_TILE, r1 = std::min<int64_t>(NO, r0 + FEDMX_TILE);
+            touched_c.clear();
+            touched_v.clear();
+            for (int64_t r = r0; r < r1; ++r) { vtx_loc[row_node[r]] = int32_t(r - r0); touched_v.push_back(row_node[r]); }
+            int nvtx = FEDMX_TILE;                       // local ids 0..127 are the tile's rows (also for a short last tile)
+            TileInfo &ti = tinfo[t];
+            ti.cell_off = int32_t(tcellv.size());
+            ti.halo_off = int32_t(thalo.size());
+            size_t maxfan = 0;
+            for (int64_t r = r0; r < r1; ++r) maxfan = std::max(maxfan, fans[row_node[r]].size());
+            for (size_t m = 0; m < maxfan; ++m)
+                for (int64_t r = r0; r < r1; ++r) {
+                    const int32_t v = row_node[r];
+                    const std::vector<Inc> &fan = fans[v];
+                    if (m >= fan.size()) continue;
+                    const int32_t c = fan[m].cell;
+                    const int32_t *cv = h_cells + 3 * int64_t(c);
+                    if (cell_loc[c] < 0) {
+                        cell_loc[c] = int32_t(tcellv.size()) - ti.cell_off;
+                        touched_c.push_back(c);
+                        unsigned long long w = 0;
+                        for (int k = 0; k < 3; ++k) {
+                            if (vtx_loc[cv[k]] < 0) {
+                                vtx_loc[cv[k]] = nvtx++;
+                                touched_v.push_back(cv[k]);
+                                thalo.push_back(cv[k]);
+                            }
+                            w |= (unsigned long long)(uint32_t(vtx_loc[cv[k]]) & 0xffffu) << (16 * k);
+                        }
+                        tcellv.push_back(w);
+                    }
+                    const int ka = (cv[0] == v) ? 0 : (cv[1] == v ? 1 : 2);
+                    const int kp = (cv[0] == fan[m].vp) ? 0 : (cv[1] == fan[m].vp ? 1 : 2);
+                    const int64_t s = r / FEDMX_SLICE, l = r % FEDMX_SLICE;
+                    inc_cell[int64_t(inc_ptr[s]) + int64_t(m) * FEDMX_SLICE + l] =
+                        uint32_t(cell_loc[c]) | (uint32_t(ka) << 12) | (uint32_t(kp) << 14);
+                }
+            ti.n_cells = int32_t(tcellv.size()) - ti.cell_off;
+            ti.n_halo = int32_t(thalo.size()) - ti.halo_off;
+            max_cells = std::max(max_cells, int(ti.n_cells));
+            max_vtx = std::max(max_vtx, nvtx);
+            if (ti.n_cells > 4095 || nvtx > 65535) tiles_ok = false;
+            for (int32_t c : touched_c) cell_loc[c] = -1;
+            for (int32_t v : touched_v) vtx_loc[v] = -1;
         }
     }
     fans.clear();
@@ -246,6 +372,19 @@ extern "C" int fedmx_mesh_set(fedmx_ctx *ctx, int n_eq, int64_t n_vertices, cons
     if ((rc = fedmx_upload(ctx, &p32, inc_vn))) return rc; S.inc_vn = p32;
     if ((rc = fedmx_upload(ctx, &pu32, inc_pack))) return rc; S.inc_pack = pu32;
     if ((rc = fedmx_upload(ctx, &pu32, row_pack))) return rc; S.row_pack = pu32;
+    if ((rc = fedmx_upload(ctx, &p32, row_node))) return rc; S.row_node = p32;
+    if (tiles_ok) {
+        TileView &T = ctx->tiles;
+        TileInfo *pti;
+        unsigned long long *pcv;
+        if ((rc = fedmx_upload(ctx, &pti, tinfo))) return rc; T.info = pti;
+        if ((rc = fedmx_upload(ctx, &p32, thalo))) return rc; T.halo = p32;
+        if ((rc = fedmx_upload(ctx, &pcv, tcellv))) return rc; T.cellv = pcv;
+        if ((rc = fedmx_upload(ctx, &pu32, inc_cell))) return rc; T.inc_cell = pu32;
+        T.n_tiles = n_tiles;
+        T.max_cells = max_cells;
+        T.max_vtx = max_vtx;
+    }
     const int NB = n_eq * n_eq;
     if ((rc = fedmx_dev_alloc(ctx, &ctx->d_val, size_t(n_slots) * NB))) return rc;
     if ((rc = fedmx_dev_alloc(ctx, &ctx->d_dinv, size_t(n_slices) * FEDMX_SLICE * NB))) return rc;
@@ -273,8 +412,9 @@ extern "C" int fedmx_matrix_get_bsr(fedmx_ctx *ctx, double *h_values) {
     FEDMX_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     FEDMX_CHECK_CUDA(ctx, cudaMemcpy(v.data(), ctx->d_val, v.size() * sizeof(double), cudaMemcpyDeviceToHost));
     const auto &rp = ctx->h_rowptr;
-    for (int64_t r = 0; r < ctx->n_owned; ++r) {
-        int64_t s = r / FEDMX_SLICE, l = r % FEDMX_SLICE;
+    for (int64_t r = 0; r < ctx->n_owned; ++r) {                       // r: node (the exported pattern is in node order)
+        const int64_t sr = ctx->h_node_row[r];
+        int64_t s = sr / FEDMX_SLICE, l = sr % FEDMX_SLICE;
         for (int32_t q = rp[r]; q < rp[r + 1]; ++q) {
             int64_t k = q - rp[r];
             const double *src = v.data() + (int64_t(ctx->h_slice_ptr[s]) + k * FEDMX_SLICE) * NB + l;
@@ -297,7 +437,10 @@ extern "C" int fedmx_dirichlet_set(fedmx_ctx *ctx, int comp, int64_t n_nodes, co
         int32_t vi = h_value_index[i];
         FEDMX_REQUIRE(ctx, v >= 0 && v < ctx->n_vertices, "fedmx_dirichlet_set: node out of range");
         FEDMX_REQUIRE(ctx, vi >= 0 && vi < FEDMX_MAX_BC - 1, "fedmx_dirichlet_set: value index out of range");
-        if (v < ctx->n_owned) row_pack[v] = (row_pack[v] & 0xffffu) | (uint32_t(vi + 1) << 16);
+        if (v < ctx->n_owned) {
+            const int32_t sr = ctx->h_node_row[v];
+            row_pack[sr] = (row_pack[sr] & 0x8000ffffu) | (uint32_t(vi + 1) << 16);
+        }
     }
     FEDMX_CHECK_CUDA(ctx, cudaMemcpy((void *)ctx->sell.row_pack, row_pack.data(), row_pack.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     ctx->bc_comp = comp;

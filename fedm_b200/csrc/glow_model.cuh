@@ -22,6 +22,7 @@
 #include "dual.cuh"
 
 struct GlowModel {
+    static constexpr bool TILED = false;
     static constexpr int MINB = 2, MINB_RES = 2;
     static constexpr unsigned ZERO_MASK = 0;
     static constexpr int NC = 0;

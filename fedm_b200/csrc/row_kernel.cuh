@@ -116,14 +116,15 @@ __global__ void __launch_bounds__(128, MINB) assemble_rows_kernel(AsmArgs A) {
     const uint32_t rp = A.S.row_pack[row];
     const int n_inc = active ? int(rp & 0xffu) : 0;
     const int diag_slot = int((rp >> 8) & 0xffu);
-    const int bc = int(rp >> 16);                   // value index + 1, 0 = unconstrained
+    const int bc = int((rp >> 16) & 0x7fffu);       // value index + 1, 0 = unconstrained (bit 31: row touches a marked facet)
     const int bc_comp = A.mp.bc_comp;
     const int64_t gbase = A.S.slice_ptr[s];
     const int64_t ibase = A.S.inc_ptr[s];
     const int width = A.S.inc_width[s];
 
+    const int32_t node = active ? A.S.row_node[row] : 0;           // storage row -> mesh node (vectors are in node order)
     Vtx<NEQ, NF, NC> va;
-    if (active) load_vertex<NEQ, NF, NC>(A, int32_t(row), va);
+    if (active) load_vertex<NEQ, NF, NC>(A, node, va);
 
     double diag[SACC ? 1 : NB], carry[SACC ? 1 : NB], R[NEQ];
     if constexpr (SACC && JAC) {
@@ -243,7 +244,7 @@ __global__ void __launch_bounds__(128, MINB) assemble_rows_kernel(AsmArgs A) {
     if (JAC) store_block<NEQ, ZMASK>(A, gbase, diag_slot, lane, dblk);
     if (A.res) {
 #pragma unroll
-        for (int k = 0; k < NEQ; ++k) A.res[int64_t(NEQ) * row + k] = R[k];
+        for (int k = 0; k < NEQ; ++k) A.res[int64_t(NEQ) * node + k] = R[k];
     }
 }
 

@@ -57,7 +57,28 @@ def set_log_level(level):
 
 
 class _MPI:
+    """dolfin.MPI over torch.distributed: one process per GPU under ``torchrun`` plays the role of ``mpirun -np N``
+    (README.md:63-67 of the reference).  The process group is created on first use when WORLD_SIZE > 1 (NCCL when a GPU is
+    present, gloo otherwise); reductions go through it, so `MPI.sum(comm, mesh.num_cells())`, `MPI.max(comm, mesh.hmax())`
+    (fedm/utils.py:22-35) give the global values."""
     comm_world = "world"
+
+    @staticmethod
+    def _dist():
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        if world <= 1:
+            return None
+        import torch
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            if torch.cuda.is_available():
+                local = int(os.environ.get("LOCAL_RANK", "0"))
+                torch.cuda.set_device(local)
+                dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            else:
+                dist.init_process_group("gloo")
+        return dist
 
     @staticmethod
     def rank(comm=None):
@@ -68,16 +89,34 @@ class _MPI:
         return int(os.environ.get("WORLD_SIZE", "1"))
 
     @staticmethod
+    def _reduce(v, op):
+        dist = _MPI._dist()
+        if dist is None:
+            return v
+        import torch
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+        t = torch.tensor([float(v)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=getattr(dist.ReduceOp, op))
+        out = float(t.item())
+        return int(round(out)) if isinstance(v, (int, np.integer)) else out
+
+    @staticmethod
     def sum(comm, v):
-        return v
+        return _MPI._reduce(v, "SUM")
 
     @staticmethod
     def max(comm, v):
-        return v
+        return _MPI._reduce(v, "MAX")
 
     @staticmethod
     def min(comm, v):
-        return v
+        return _MPI._reduce(v, "MIN")
+
+    @staticmethod
+    def barrier(comm=None):
+        dist = _MPI._dist()
+        if dist is not None:
+            dist.barrier()
 
 
 MPI = _MPI()
@@ -131,7 +170,11 @@ class Mesh:
         return _Topology(2)
 
     def num_cells(self):
-        return self.tri.num_cells
+        """Local cell count, as for dolfin's distributed mesh: under torchrun every rank keeps the whole mesh (vectors are
+        replicated, only the solves are partitioned), so the cells are attributed to the ranks in equal contiguous shares
+        and `MPI.sum(comm, mesh.num_cells())` (fedm/utils.py:23) is the global count."""
+        n, size, rank = self.tri.num_cells, MPI.size(), MPI.rank()
+        return (n * (rank + 1)) // size - (n * rank) // size
 
     def num_vertices(self):
         return self.tri.num_vertices
@@ -637,11 +680,22 @@ class DirichletBC:
         self.nodes = np.array(sorted(nodes), dtype=np.int32)
 
     def current_value(self):
+        """One value per condition (the device path applies Dirichlet data as a scalar per marked set).  Constants and
+        x-independent Expressions -- every condition in FEDM's scripts -- are exact; spatially varying data would silently be
+        collapsed to its value at the origin, so it is refused."""
         v = self.value
         if isinstance(v, Constant):
             return v.values[0]
         if isinstance(v, Expression):
+            if self.nodes.size:
+                xy = self.space.mesh().tri.coords[self.nodes[[0, self.nodes.size // 2, -1]]]
+                vals = [v.value_at(float(p[0]), float(p[1])) for p in xy]
+                if max(vals) - min(vals) > 1e-12 * max(1.0, max(abs(t) for t in vals)):
+                    raise NotImplementedError("DirichletBC: spatially varying boundary values are not supported on the device path")
+                return float(vals[0])
             return float(v)
+        if isinstance(v, Function):
+            raise NotImplementedError("DirichletBC: Function-valued boundary data is not supported on the device path")
         return float(v)
 
     def apply(self, *tensors):
@@ -679,9 +733,19 @@ def _quadrature_degree():
 
 
 def _solve_linear(a_form, L_form, u, bcs, tight=True, ident_zeros=False):
+    """Stands in for the direct (MUMPS / LU) solves behind solve(), project(), Poisson_solver, Normal_vector and
+    BoundaryGradient: Newton on the linear residual with tight Krylov tolerances.  A direct solver cannot return an
+    unconverged field, so a stalled Krylov solve raises here instead of passing silently."""
     residual = action(a_form, u) - L_form
-    prob = get_backend().compile(residual, u, bcs, _quadrature_degree(), ident_zeros=ident_zeros)
-    prob.solve_newton(u, rtol=1e-12, atol=0.0, max_it=3, linear_solver="mumps", raise_on_failure=False)
+    prob = get_backend().compile(residual, u, bcs, _quadrature_degree(), ident_zeros=ident_zeros, reuse=True)
+    its, converged = prob.solve_newton(u, rtol=1e-12, atol=0.0, max_it=3, linear_solver="mumps", raise_on_failure=False)
+    if not converged:
+        res = prob.last_result
+        fn0, fn = (getattr(res, "fnorm0", None), getattr(res, "fnorm", None)) if res is not None and not isinstance(res, tuple) else (None, None)
+        # max_it reached on a linear problem is fine when the residual has dropped to round-off (rtol 1e-12 may be
+        # unreachable for an ill-scaled right-hand side); anything else is a failed linear solve
+        if fn0 is None or not (fn <= 1e-9 * fn0 or fn <= 1e-14):
+            raise RuntimeError(f"linear solve did not converge ({its} Newton iterations, |r0| = {fn0}, |r| = {fn})")
 
 
 def solve(A, x, b, *args):
@@ -752,9 +816,10 @@ class PETScSNESSolver:
             raise NotImplementedError("PETScSNESSolver.solve: the problem must expose .linear_form/.bcs (FEDM's Problem class)")
         u = x.function
         key = id(problem)
-        if key not in self._compiled:
-            self._compiled[key] = get_backend().compile(F, u, list(getattr(problem, "bcs", [])), _quadrature_degree())
-        prob = self._compiled[key]
+        # the entry keeps a reference to the problem object: its id cannot be recycled for another Problem while cached
+        if key not in self._compiled or self._compiled[key][0] is not problem:
+            self._compiled[key] = (problem, get_backend().compile(F, u, list(getattr(problem, "bcs", [])), _quadrature_degree()))
+        prob = self._compiled[key][1]
         p = self.parameters
         res = prob.solve_newton(u, rtol=p["relative_tolerance"], atol=p["absolute_tolerance"], stol=p["solution_tolerance"],
                                 max_it=p["maximum_iterations"], linear_solver=p["linear_solver"],

@@ -69,7 +69,7 @@ class DryRunBackend:
     def zeros(self, n, space=None):
         return HostStore(n)
 
-    def compile(self, residual, u, bcs, quad_degree, ident_zeros=False):
+    def compile(self, residual, u, bcs, quad_degree, ident_zeros=False, reuse=False):
         so = CompiledForm(residual, u, quad_degree).build()
         self.built.append(so.name)
         return _Recorded(so)

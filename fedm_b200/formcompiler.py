@@ -444,12 +444,16 @@ class CompiledForm:
         cu, so = CACHE / f"form_{self.key}.cu", CACHE / f"form_{self.key}.so"
         if so.exists():
             return so
-        cu.write_text(self.source)
+        tmp = f"{so}.{os.getpid()}.tmp"                     # per process: ranks compiling the same form must not share it
+        if not cu.exists() or cu.read_text() != self.source:
+            cu_tmp = f"{cu}.{os.getpid()}.tmp"
+            Path(cu_tmp).write_text(self.source)
+            os.replace(cu_tmp, cu)
         nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
         cmd = [nvcc, "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
-               "-shared", "-I", str(HERE / "csrc"), "-o", str(so) + ".tmp", str(cu)]
+               "-shared", "-I", str(HERE / "csrc"), "-o", tmp, str(cu)]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
             raise RuntimeError(f"form compiler: nvcc failed for {cu}\n{res.stderr[-4000:]}")
-        os.replace(str(so) + ".tmp", so)
+        os.replace(tmp, so)
         return so

@@ -348,4 +348,6 @@ def h211b_step(dt, dt_old, err, tol, dt_min, dt_max):
 def pid_step(dt, err, tol, dt_min, dt_max):
     """``adaptive_timestep`` (fedm/functions.py:915-927) through the library's host libm implementation."""
     e = (C.c_double * 3)(*[float(v) for v in err])
+    if e[0] == 0.0 or e[2] == 0.0:
+        raise ZeroDivisionError("float division by zero")          # what the reference's Python expression raises
     return float(_l.load().fedmx_pid_step(dt, e, tol, dt_min, dt_max))

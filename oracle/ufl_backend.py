@@ -304,5 +304,5 @@ class NumpyBackend:
     def zeros(self, n, space=None):
         return NumpyStore(n)
 
-    def compile(self, residual, u, bcs, quad_degree, ident_zeros=False):
+    def compile(self, residual, u, bcs, quad_degree, ident_zeros=False, reuse=False):
         return CompiledProblem(residual, u, bcs, quad_degree, ident_zeros)

@@ -168,3 +168,17 @@ def test_partitioned_run_matches_fixture(world):
         r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
         assert "PASS" in r.stdout
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_user_script_runs_partitioned_under_torchrun(world):
+    """`torchrun -n N examples/streamer_discharge.py` = the reference's `mpirun -np N python3 fedm-streamer.py`: the shim
+    partitions every solve; result == 1-GPU run to 1e-8, identical on all ranks, MPI.sum/max global (tools/script_mgpu_check.py)."""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(29560 + world), str(ROOT / "tools" / "script_mgpu_check.py")]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "PASS" in r.stdout

@@ -118,3 +118,23 @@ def test_peer_staging_offsets_put_every_segment_where_the_receiver_unpacks_it(wo
         vec = np.zeros(lm.num_vertices)
         vec[lm.recv_nodes] = staging[lm.rank]
         assert np.array_equal(vec[lm.n_owned:], gvals[lm.local_to_global[lm.n_owned:]])
+
+
+def test_rcb_partition_is_balanced_and_compact():
+    """Recursive coordinate bisection (general / graded meshes): +-1 balance for any rank count, sub-domains are
+    coordinate boxes, and the ghost layer is much smaller than for slabs when there are many ranks."""
+    from fedm_b200.mesh import rectangle
+    from fedm_b200.partition import build_local_mesh, partition_owner, rcb_owner, strip_owner
+    m = rectangle((0.0, 0.0), (1.0, 1.0), 48, 48, "right", map_x=lambda s: s ** 2)
+    for world in (2, 3, 5, 8, 16):
+        owner = rcb_owner(m.coords, world)
+        counts = np.bincount(owner, minlength=world)
+        assert counts.max() - counts.min() <= 1 and counts.sum() == m.num_vertices
+    fv, fm = m.exterior_facets(), np.ones(len(m.exterior_facets()), dtype=np.int32)
+    ghosts = {}
+    for name, owner in (("rcb", rcb_owner(m.coords, 16)), ("strip", strip_owner(m.coords, 16))):
+        ghosts[name] = sum(build_local_mesh(m.coords, m.cells, fv, fm, owner, r, 16).num_vertices -
+                           build_local_mesh(m.coords, m.cells, fv, fm, owner, r, 16).n_owned for r in range(0, 16, 5))
+    assert ghosts["rcb"] < 0.6 * ghosts["strip"]
+    assert np.array_equal(partition_owner(m.coords, 4, "strip"), strip_owner(m.coords, 4, axis=1))
+    assert np.array_equal(partition_owner(m.coords, 16, "auto"), rcb_owner(m.coords, 16))
