@@ -65,9 +65,17 @@ struct StreamerModel {
         stage_store(sm, i, stage_load(A, node));
     }
 
+    // Cell record in registers: computed for two cells at a time (two independent dependency chains through sqrt / log /
+    // exp keep the FP64 pipe fed), then stored.
     template <bool JAC>
-    static __device__ __forceinline__ void cell(const ModelParams &mp, const TileSmem &sm, int l0, int l1, int l2, int c) {
+    struct CellRec { double f[JAC ? NREC_JAC : NREC_RES]; };
+
+    template <bool JAC>
+    static __device__ __forceinline__ CellRec<JAC> cell_compute(const ModelParams &mp, const TileSmem &sm, int l0, int l1, int l2) {
+        CellRec<JAC> R;
         const double r0 = sm.v(0, l0), z0 = sm.v(1, l0), r1 = sm.v(0, l1), z1 = sm.v(1, l1), r2 = sm.v(0, l2), z2 = sm.v(1, l2);
+        const double ue0 = sm.v(3, l0), ue1 = sm.v(3, l1), ue2 = sm.v(3, l2);
+        const double ph0 = sm.v(4, l0), ph1 = sm.v(4, l1), ph2 = sm.v(4, l2);
         const double e1r = r1 - r0, e1z = z1 - z0, e2r = r2 - r0, e2z = z2 - z0;
         const double det = e1r * e2z - e1z * e2r;
         const double inv = 1.0 / det;
@@ -75,8 +83,6 @@ struct StreamerModel {
         gr[1] = e2z * inv; gz[1] = -e2r * inv;
         gr[2] = -e1z * inv; gz[2] = e1r * inv;
         gr[0] = -gr[1] - gr[2]; gz[0] = -gz[1] - gz[2];
-        const double ue0 = sm.v(3, l0), ue1 = sm.v(3, l1), ue2 = sm.v(3, l2);
-        const double ph0 = sm.v(4, l0), ph1 = sm.v(4, l1), ph2 = sm.v(4, l2);
         const double Gr = ph0 * gr[0] + ph1 * gr[1] + ph2 * gr[2], Gz = ph0 * gz[0] + ph1 * gz[1] + ph2 * gz[2];
         const double Hr = ue0 * gr[0] + ue1 * gr[1] + ue2 * gr[2], Hz = ue0 * gz[0] + ue1 * gz[1] + ue2 * gz[2];
         const double Em = sqrt(Gr * Gr + Gz * Gz);
@@ -91,29 +97,41 @@ struct StreamerModel {
         const double Pr = -D * Hr + mu * Gr, Pz = -D * Hz + mu * Gz;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            sm.r(k, c) = Pr * gr[k] + Pz * gz[k];
-            sm.r(3 + k, c) = Gr * gr[k] + Gz * gz[k];
+            R.f[k] = Pr * gr[k] + Pz * gz[k];
+            R.f[3 + k] = Gr * gr[k] + Gz * gz[k];
         }
-        sm.r(6, c) = alpha * mu * Em;
-        sm.r(7, c) = fabs(det) * (1.0 / 6.0) * kTwoPi;
-        if (JAC) {
+        R.f[6] = alpha * mu * Em;
+        R.f[7] = fabs(det) * (1.0 / 6.0) * kTwoPi;
+        if constexpr (JAC) {
             const double dmu = mp.p[1] * mu * iEm;
             const double dD = mp.p[3] * D * iEm;
             const double dalpha = (-3.0 * mp.p[5] * iE3 * iEm + pre * mp.p[6] * iEm * iEm) * ex;
             const double Qr = -dD * Hr + dmu * Gr, Qz = -dD * Hz + dmu * Gz;
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                sm.r(8 + k, c) = Qr * gr[k] + Qz * gz[k];
-                sm.r(11 + k, c) = gr[k] * gr[k] + gz[k] * gz[k];
+                R.f[8 + k] = Qr * gr[k] + Qz * gz[k];
+                R.f[11 + k] = gr[k] * gr[k] + gz[k] * gz[k];
             }
-            sm.r(14, c) = gr[0] * gr[1] + gz[0] * gz[1];
-            sm.r(15, c) = gr[0] * gr[2] + gz[0] * gz[2];
-            sm.r(16, c) = gr[1] * gr[2] + gz[1] * gz[2];
-            sm.r(17, c) = iEm;
-            sm.r(18, c) = mu;
-            sm.r(19, c) = D;
-            sm.r(20, c) = dalpha * mu * Em + alpha * dmu * Em + alpha * mu;
+            R.f[14] = gr[0] * gr[1] + gz[0] * gz[1];
+            R.f[15] = gr[0] * gr[2] + gz[0] * gz[2];
+            R.f[16] = gr[1] * gr[2] + gz[1] * gz[2];
+            R.f[17] = iEm;
+            R.f[18] = mu;
+            R.f[19] = D;
+            R.f[20] = dalpha * mu * Em + alpha * dmu * Em + alpha * mu;
         }
+        return R;
+    }
+
+    template <bool JAC>
+    static __device__ __forceinline__ void cell_store(const TileSmem &sm, int c, const CellRec<JAC> &R) {
+#pragma unroll
+        for (int k = 0; k < (JAC ? NREC_JAC : NREC_RES); ++k) sm.r(k, c) = R.f[k];
+    }
+
+    template <bool JAC>
+    static __device__ __forceinline__ void cell(const ModelParams &mp, const TileSmem &sm, int l0, int l1, int l2, int c) {
+        cell_store<JAC>(sm, c, cell_compute<JAC>(mp, sm, l0, l1, l2));
     }
 
     static __device__ __forceinline__ void load_staged(const TileSmem &sm, int l, V &v) {

@@ -51,15 +51,16 @@ struct SellView {
 // Cell batches of the tiled assembly kernel: tile t = storage rows [128 t, 128 t + 128).  Its vertex set is the tile's own
 // nodes (local index = row - 128 t) followed by `n_halo` ring vertices; its cells are all cells incident to its rows.
 struct TileInfo {
-    int32_t cell_off, n_cells;   // into cellv
-    int32_t halo_off, n_halo;    // into halo
+    int32_t n_cells, n_halo;
 };
 struct TileView {
     int64_t n_tiles = 0;
     int max_cells = 0, max_vtx = 0;
+    int64_t cell_stride = 0, halo_stride = 0;    // tile t: cellv[t*cell_stride ...], halo[t*halo_stride ...] (fixed strides: the
+                                                 // kernel can issue these loads without waiting for the tile descriptor)
     const TileInfo *info = nullptr;
-    const int32_t *halo = nullptr;          // node ids of the ring vertices
-    const unsigned long long *cellv = nullptr;   // per cell: local vertex indices v0 | v1<<16 | v2<<32
+    const int32_t *halo = nullptr;          // node ids of the ring vertices (padding: -1)
+    const unsigned long long *cellv = nullptr;   // per cell: local vertex indices v0 | v1<<16 | v2<<32 (padding: 0)
     const uint32_t *inc_cell = nullptr;     // fan layout (like inc_pack): local cell | ka<<12 | kp<<14  (ka/kp: position of the row's
                                             // node / of the fan's "previous" vertex inside the cell)
 };

@@ -291,8 +291,8 @@ extern "C" int fedmx_mesh_set(fedmx_ctx *ctx, int n_eq, int64_t n_vertices, cons
     // the ring of vertices outside the tile, and per fan entry (local cell, position of the row's node, position of vp)
     const int64_t n_tiles = (NO + FEDMX_TILE - 1) / FEDMX_TILE;
     std::vector<TileInfo> tinfo(n_tiles);
-    std::vector<int32_t> thalo;
-    std::vector<unsigned long long> tcellv;
+    std::vector<std::vector<int32_t>> thalo_t(n_tiles);
+    std::vector<std::vector<unsigned long long>> tcellv_t(n_tiles);
     int max_cells = 0, max_vtx = 0;
     bool tiles_ok = true;
     {
@@ -304,8 +304,8 @@ extern "C" int fedmx_mesh_set(fedmx_ctx *ctx, int n_eq, int64_t n_vertices, cons
             for (int64_t r = r0; r < r1; ++r) { vtx_loc[row_node[r]] = int32_t(r - r0); touched_v.push_back(row_node[r]); }
             int nvtx = FEDMX_TILE;                       // local ids 0..127 are the tile's rows (also for a short last tile)
             TileInfo &ti = tinfo[t];
-            ti.cell_off = int32_t(tcellv.size());
-            ti.halo_off = int32_t(thalo.size());
+            std::vector<int32_t> &thalo = thalo_t[t];
+            std::vector<unsigned long long> &tcellv = tcellv_t[t];
             size_t maxfan = 0;
             for (int64_t r = r0; r < r1; ++r) maxfan = std::max(maxfan, fans[row_node[r]].size());
             for (size_t m = 0; m < maxfan; ++m)
@@ -316,7 +316,7 @@ extern "C" int fedmx_mesh_set(fedmx_ctx *ctx, int n_eq, int64_t n_vertices, cons
                     const int32_t c = fan[m].cell;
                     const int32_t *cv = h_cells + 3 * int64_t(c);
                     if (cell_loc[c] < 0) {
-                        cell_loc[c] = int32_t(tcellv.size()) - ti.cell_off;
+                        cell_loc[c] = int32_t(tcellv.size());
                         touched_c.push_back(c);
                         unsigned long long w = 0;
                         for (int k = 0; k < 3; ++k) {
@@ -335,8 +335,8 @@ extern "C" int fedmx_mesh_set(fedmx_ctx *ctx, int n_eq, int64_t n_vertices, cons
                     inc_cell[int64_t(inc_ptr[s]) + int64_t(m) * FEDMX_SLICE + l] =
                         uint32_t(cell_loc[c]) | (uint32_t(ka) << 12) | (uint32_t(kp) << 14);
                 }
-            ti.n_cells = int32_t(tcellv.size()) - ti.cell_off;
-            ti.n_halo = int32_t(thalo.size()) - ti.halo_off;
+            ti.n_cells = int32_t(tcellv.size());
+            ti.n_halo = int32_t(thalo.size());
             max_cells = std::max(max_cells, int(ti.n_cells));
             max_vtx = std::max(max_vtx, nvtx);
             if (ti.n_cells > 4095 || nvtx > 65535) tiles_ok = false;
@@ -377,6 +377,16 @@ extern "C" int fedmx_mesh_set(fedmx_ctx *ctx, int n_eq, int64_t n_vertices, cons
         TileView &T = ctx->tiles;
         TileInfo *pti;
         unsigned long long *pcv;
+        int max_halo = 0;
+        for (const TileInfo &ti : tinfo) max_halo = std::max(max_halo, int(ti.n_halo));
+        T.cell_stride = (max_cells + 15) & ~15;
+        T.halo_stride = (max_halo + 15) & ~15;
+        std::vector<int32_t> thalo(size_t(n_tiles) * T.halo_stride, -1);
+        std::vector<unsigned long long> tcellv(size_t(n_tiles) * T.cell_stride, 0ull);
+        for (int64_t t = 0; t < n_tiles; ++t) {
+            std::copy(thalo_t[t].begin(), thalo_t[t].end(), thalo.begin() + t * T.halo_stride);
+            std::copy(tcellv_t[t].begin(), tcellv_t[t].end(), tcellv.begin() + t * T.cell_stride);
+        }
         if ((rc = fedmx_upload(ctx, &pti, tinfo))) return rc; T.info = pti;
         if ((rc = fedmx_upload(ctx, &p32, thalo))) return rc; T.halo = p32;
         if ((rc = fedmx_upload(ctx, &pcv, tcellv))) return rc; T.cellv = pcv;

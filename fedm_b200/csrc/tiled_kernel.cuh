@@ -55,15 +55,21 @@ struct RowPrefetch {
     uint32_t rp, pack0, cw0;
     int32_t gbase, ibase;
 };
+// volatile: the compiler must neither sink these loads to their first use (two barriers later) nor merge them away
+__device__ __forceinline__ uint32_t ldg_now(const void *p) {
+    uint32_t v;
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ RowPrefetch row_prefetch(const RowCtx &C, int64_t row) {
     RowPrefetch r;
     const int64_t s = row / FEDMX_SLICE;
-    r.rp = C.row_pack[row];
-    r.gbase = C.slice_ptr[s];
-    r.ibase = C.inc_ptr[s];
+    r.rp = ldg_now(C.row_pack + row);
+    r.gbase = int32_t(ldg_now(C.slice_ptr + s));
+    r.ibase = int32_t(ldg_now(C.inc_ptr + s));
     const int64_t e = int64_t(r.ibase) + (row % FEDMX_SLICE);
-    r.pack0 = C.inc_pack[e];                     // every owned row has at least one incident cell; padding rows read slot 0
-    r.cw0 = C.inc_cell[e];
+    r.pack0 = ldg_now(C.inc_pack + e);           // every owned row has at least one incident cell
+    r.cw0 = ldg_now(C.inc_cell + e);
     return r;
 }
 
@@ -189,6 +195,7 @@ __global__ void __launch_bounds__(FEDMX_TILE, MINB) assemble_tiled_kernel(TiledA
     const bool active = row < A.S.n_rows;
     // ---- issue every index load up front: tile descriptor, own node id, row descriptor + first fan entry, the thread's cell
     // words and its halo vertex id; they are consumed phases later
+    // (the cell words and ring-vertex ids of a tile sit at fixed strides, so none of these loads waits for the descriptor)
     const TileInfo ti = P.T.info[tile];
     const int32_t node = active ? A.S.row_node[row] : -1;
     RowCtx C;
@@ -203,9 +210,9 @@ __global__ void __launch_bounds__(FEDMX_TILE, MINB) assemble_tiled_kernel(TiledA
 #pragma unroll
     for (int k = 0; k < CPT; ++k) {
         const int c = tid + k * FEDMX_TILE;
-        cwords[k] = c < ti.n_cells ? P.T.cellv[ti.cell_off + c] : 0ull;
+        cwords[k] = c < P.T.cell_stride ? P.T.cellv[tile * P.T.cell_stride + c] : 0ull;          // padding words are 0
     }
-    const int32_t hnode = tid < ti.n_halo ? P.T.halo[ti.halo_off + tid] : -1;
+    const int32_t hnode = tid < P.T.halo_stride ? P.T.halo[tile * P.T.halo_stride + tid] : -1;      // padding ids are -1
     if (tid < FEDMX_MAX_BC) s_bc[tid] = A.mp.bc_values[tid];
 
     // ---- phase V: own nodes (local id = tid), then the halo ring
@@ -215,11 +222,19 @@ __global__ void __launch_bounds__(FEDMX_TILE, MINB) assemble_tiled_kernel(TiledA
         if (active) Model::stage_store(sm, tid, own);
         if (hnode >= 0) Model::stage_store(sm, FEDMX_TILE + tid, ring);
     }
-    for (int h = tid + FEDMX_TILE; h < ti.n_halo; h += FEDMX_TILE) Model::stage(A, P.T.halo[ti.halo_off + h], sm, FEDMX_TILE + h);
+    for (int h = tid + FEDMX_TILE; h < ti.n_halo; h += FEDMX_TILE) Model::stage(A, P.T.halo[tile * P.T.halo_stride + h], sm, FEDMX_TILE + h);
     __syncthreads();
     // ---- phase C: cell records
+    {   // cells tid and tid + 128 together (every tile has more than 256 cells unless it is a ragged last one): the word of an
+        // absent cell is 0 = three times local vertex 0, a degenerate but harmless cell whose record is not stored
+        const unsigned long long w0 = cwords[0], w1 = cwords[1];
+        const auto r0 = Model::template cell_compute<JAC>(A.mp, sm, int(w0 & 0xffffu), int((w0 >> 16) & 0xffffu), int((w0 >> 32) & 0xffffu));
+        const auto r1 = Model::template cell_compute<JAC>(A.mp, sm, int(w1 & 0xffffu), int((w1 >> 16) & 0xffffu), int((w1 >> 32) & 0xffffu));
+        if (tid < ti.n_cells) { sm.cellv[tid] = w0; Model::template cell_store<JAC>(sm, tid, r0); }
+        if (tid + FEDMX_TILE < ti.n_cells) { sm.cellv[tid + FEDMX_TILE] = w1; Model::template cell_store<JAC>(sm, tid + FEDMX_TILE, r1); }
+    }
 #pragma unroll
-    for (int k = 0; k < CPT; ++k) {
+    for (int k = 2; k < CPT; ++k) {
         const int c = tid + k * FEDMX_TILE;
         if (c < ti.n_cells) {
             const unsigned long long w = cwords[k];
@@ -228,7 +243,7 @@ __global__ void __launch_bounds__(FEDMX_TILE, MINB) assemble_tiled_kernel(TiledA
         }
     }
     for (int c = tid + CPT * FEDMX_TILE; c < ti.n_cells; c += FEDMX_TILE) {
-        const unsigned long long w = P.T.cellv[ti.cell_off + c];
+        const unsigned long long w = P.T.cellv[tile * P.T.cell_stride + c];
         sm.cellv[c] = w;
         Model::template cell<JAC>(A.mp, sm, int(w & 0xffffu), int((w >> 16) & 0xffffu), int((w >> 32) & 0xffffu), c);
     }
