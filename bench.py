@@ -134,6 +134,9 @@ def main():
     ap.add_argument("--ref-budget-s", type=float, default=200.0, help="wall-clock budget of the CPU arm's timed steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the post-run parity trajectory (1-GPU / exact-solve re-run)")
+    ap.add_argument("--precond", default="amg", choices=["amg", "ilu0", "bjacobi"],
+                    help="amg (default): two-stage AMG + node-block Jacobi; ilu0: the reference test's literal PC (PETSc default for "
+                         "linear_solver='gmres': ILU(0), block Jacobi across GPUs) -- reports its Krylov iterations per step")
     ap.add_argument("--profile-detail", action="store_true", help="nested event timing of multigrid levels and collectives")
     args = ap.parse_args()
 
@@ -157,7 +160,7 @@ def main():
     from fedm_b200.streamer import StreamerCase
 
     t_setup = time.time()
-    case = StreamerCase(n=args.n, device=local_rank, world=world, rank=rank)
+    case = StreamerCase(n=args.n, device=local_rank, world=world, rank=rank, precond=args.precond)
     case.set_initial_state(bench_initial_potential=True)
     setup_s = time.time() - t_setup
     hot = case.hot
@@ -230,7 +233,7 @@ def main():
     parity = None
     if not args.no_parity:
         kw = dict(ksp_rtol=1e-13, ksp_max_it=50000) if world == 1 else {}
-        ref_case = StreamerCase(n=args.n, device=local_rank, **kw)
+        ref_case = StreamerCase(n=args.n, device=local_rank, **kw)           # always the default preconditioner
         ref_case.set_initial_state(bench_initial_potential=True)
         ref_case.run(max_steps=steps_taken)
         Xr = ref_case.x_new.view(-1, 3)
@@ -263,7 +266,9 @@ def main():
         "dtype": "f64", "data": "synthetic",
         "config": workload_config(args.n),
         "solver": {"linear": "GMRES(30), classical Gram-Schmidt with one reduction per iteration, left PC, rtol 1e-5",
-                   "preconditioner": "two-stage: AMG V(1,1) on the potential block + node-block Jacobi",
+                   "preconditioner": {"amg": "two-stage: AMG V(1,1) on the potential block + node-block Jacobi",
+                                      "ilu0": "ILU(0) per GPU block (multicolour ordering), block Jacobi across GPUs: the reference test's PC",
+                                      "bjacobi": "node-block Jacobi"}[args.precond],
                    "matrix_format": "SELL-32 3x3 node blocks, FP64; the structurally zero block entry (1 of 9) is kept in the "
                                     "exported dolfin pattern but not streamed",
                    "parallelism": f"vertex partition x{world}" if world > 1 else "single GPU"},

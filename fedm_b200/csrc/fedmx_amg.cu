@@ -484,6 +484,7 @@ int fedmx_apply_dinv(fedmx_ctx *ctx, const double *d_r, double *d_z);
 int fedmx_precond_apply(fedmx_ctx *ctx, const double *d_r, double *d_z) {
     int rc;
     if (ctx->precond_kind == 0) return fedmx_apply_dinv(ctx, d_r, d_z);
+    if (ctx->precond_kind == 2) return fedmx_ilu0_solve_internal(ctx, d_r, d_z);
     ProfScope prof(ctx, FEDMX_PROF_PRECOND);
     AmgLevel &l0 = ctx->amg_levels[0];
     const int comp = ctx->amg_comp;
@@ -591,7 +592,7 @@ extern "C" int fedmx_amg_set_coarse(fedmx_ctx *ctx, int n, const double *h_inver
 
 extern "C" int fedmx_precond_set(fedmx_ctx *ctx, int kind, int comp, int nu) {
     if (!ctx) return FEDMX_EINVAL;
-    FEDMX_REQUIRE(ctx, kind == 0 || kind == 1, "fedmx_precond_set: kind must be 0 (block-Jacobi) or 1 (two-stage AMG)");
+    FEDMX_REQUIRE(ctx, kind == 0 || kind == 1 || kind == 2, "fedmx_precond_set: kind must be 0 (block-Jacobi), 1 (two-stage AMG) or 2 (ILU(0))");
     if (kind == 1) {
         FEDMX_REQUIRE(ctx, !ctx->amg_levels.empty() && ctx->amg_coarse_inv, "fedmx_precond_set: upload the AMG hierarchy first");
         FEDMX_REQUIRE(ctx, comp >= 0 && comp < ctx->n_eq && nu >= 1 && nu <= 4, "fedmx_precond_set: bad component / sweeps");
@@ -600,6 +601,7 @@ extern "C" int fedmx_precond_set(fedmx_ctx *ctx, int kind, int comp, int nu) {
     ctx->amg_comp = comp;
     ctx->amg_nu = nu;
     ctx->coarse_first = -1;
+    if (kind == 2 && ctx->d_val) return fedmx_ilu0_factor_internal(ctx);     // factor the matrix that is assembled right now
     return FEDMX_OK;
 }
 

@@ -26,6 +26,7 @@ extern "C" int fedmx_ctx_destroy(fedmx_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     fedmx_peer_destroy(ctx);
     fedmx_comm_destroy_internal(ctx);
+    fedmx_ilu0_free(ctx);
     for (void *p : ctx->owned_device) cudaFree(p);
     for (void *p : ctx->amg_device) cudaFree(p);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);

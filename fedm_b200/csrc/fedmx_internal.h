@@ -127,6 +127,8 @@ struct PeerState {
     int *h_err = nullptr, *d_err = nullptr;
 };
 
+struct IluPlan;
+
 struct fedmx_ctx {
     int device = 0;
     cudaStream_t stream = 0;
@@ -169,7 +171,8 @@ struct fedmx_ctx {
     double *d_hess = nullptr;    // small device scalars for GMRES
     double *h_pinned = nullptr;  // pinned host scratch
     int64_t red_blocks = 0;
-    // preconditioner: 0 = node-block Jacobi, 1 = two-stage (AMG on component amg_comp + block Jacobi)
+    // preconditioner: 0 = node-block Jacobi, 1 = two-stage (AMG on component amg_comp + block Jacobi), 2 = multicolour ILU(0)
+    IluPlan *ilu = nullptr;
     int newton_expected_its = 0;   // Newton iterations of the previous converged solve (predictor for speculative J assembly)
     int precond_kind = 0, amg_comp = 0, amg_nu = 1;
     std::vector<AmgLevel> amg_levels;
@@ -258,4 +261,7 @@ int fedmx_peer_halo_exchange(fedmx_ctx *ctx, double *d_vec, int n_comp);
 int fedmx_peer_allreduce(fedmx_ctx *ctx, double *d_buf, int64_t n);
 int fedmx_peer_destroy(fedmx_ctx *ctx);
 int fedmx_comm_destroy_internal(fedmx_ctx *ctx);
+int fedmx_ilu0_factor_internal(fedmx_ctx *ctx);
+int fedmx_ilu0_solve_internal(fedmx_ctx *ctx, const double *d_r, double *d_z);
+void fedmx_ilu0_free(fedmx_ctx *ctx);
 double *fedmx_peer_big_buffer(fedmx_ctx *ctx, int64_t n);

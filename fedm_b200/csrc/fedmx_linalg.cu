@@ -421,6 +421,7 @@ int fedmx_update_block_jacobi(fedmx_ctx *ctx) {
     }
     ctx->launches++;
     FEDMX_CHECK_CUDA(ctx, cudaGetLastError());
+    if (ctx->precond_kind == 2) return fedmx_ilu0_factor_internal(ctx);      // new matrix values: new ILU(0) factors
     return FEDMX_OK;
 }
 

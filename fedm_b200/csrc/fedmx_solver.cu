@@ -65,6 +65,9 @@ int gmres_impl(fedmx_ctx *ctx, const double *d_b, double *d_x, int restart, doub
             if (multi && (rc = fedmx_halo_exchange_internal(ctx, Vk, ctx->n_eq))) return rc;
             if (ctx->precond_kind == 0) {
                 if ((rc = fedmx_spmv_precond(ctx, Vk, w, true))) return rc;       // block Jacobi fused into the SpMV epilogue
+            } else if (ctx->precond_kind == 2) {
+                if ((rc = fedmx_spmv_precond(ctx, Vk, ctx->d_tmp, false))) return rc;
+                if ((rc = fedmx_ilu0_solve_internal(ctx, ctx->d_tmp, w))) return rc;   // w = (LU)^-1 A v
             } else {
                 if ((rc = fedmx_two_stage_after_spmv(ctx, Vk, w))) return rc;
             }

@@ -11,6 +11,11 @@ from ..formcompiler import CompiledForm
 
 
 class TorchStore:
+    """Device vector of the shim.  torch only owns the buffer and does the BLAS-1 style updates (axpy, scale); everything the
+    reference's hot path does on dof vectors -- df.norm (fedm/functions.py:1062-1064), FunctionAssigner.assign (:1050) and
+    np.interp (:627-636) -- goes through the library's kernels (fixed-order reductions, bit-exact interpolation)."""
+    util = None                 # utility HotPath context of the backend (set by CudaBackend)
+
     def __init__(self, n, device):
         self.t = torch.zeros(n, dtype=torch.float64, device=device)
 
@@ -25,7 +30,7 @@ class TorchStore:
         return self.t.numel()
 
     def norm2(self):
-        return float(torch.linalg.vector_norm(self.t))
+        return TorchStore.util.norm2(self.t, self.t.numel())           # fedmx_norm2: two-stage fixed-order reduction
 
     def clone(self):
         s = TorchStore(0, self.t.device)
@@ -48,7 +53,22 @@ class TorchStore:
         pass
 
     def strided_copy_from(self, src, sstride, soff, dstride, doff, n):
-        self.t[doff:doff + n * dstride:dstride] = src.t[soff:soff + n * sstride:sstride]
+        TorchStore.util.strided_copy(src.t, sstride, soff, self.t, dstride, doff, n)       # fedmx_strided_copy
+
+    def interp_from(self, src, kx, ky, divisor=1.0):
+        """self = np.interp(src, kx, ky) / divisor on the device (fedmx_interp_table, bit-exact with numpy)."""
+        key = (id(kx), id(ky), len(kx))
+        tabs = TorchStore._tables.get(key)
+        if tabs is None or tabs[0] is not kx:
+            dev = self.t.device
+            tabs = (kx, torch.from_numpy(np.ascontiguousarray(kx, dtype=np.float64)).to(dev),
+                    torch.from_numpy(np.ascontiguousarray(ky, dtype=np.float64)).to(dev))
+            if len(TorchStore._tables) > 256:
+                TorchStore._tables.clear()
+            TorchStore._tables[key] = tabs
+        TorchStore.util.interp_table(src.t, tabs[1], tabs[2], self.t, divisor=float(divisor))
+
+    _tables = {}
 
 
 class CudaProblem:
@@ -211,6 +231,10 @@ class CudaBackend:
         self.device_index = device_index
         self.device = torch.device("cuda", device_index)
         torch.cuda.set_device(self.device)
+        # utility context for vector kernels that need no mesh of their own (norms, strided copies, table interpolation)
+        util = hp.HotPath(device_index)
+        util.set_mesh(1, np.array([[0.0, 0.0], [1.0, 0.0], [0.0, 1.0]]), np.array([[0, 1, 2]], dtype=np.int32))
+        TorchStore.util = self.util = util
         self._cache = {}                 # structurally identical linear problems (project / Poisson_solver in a time loop)
 
     def zeros(self, n, space=None):

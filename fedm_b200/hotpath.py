@@ -198,6 +198,22 @@ class HotPath:
     def use_block_jacobi(self):
         self._ck(self.lib.fedmx_precond_set(self.h, 0, 0, 1))
 
+    def use_ilu0(self):
+        """PETSc's default PC of the reference test's KSP: ILU(0) on this rank's diagonal block (multicolour ordering)."""
+        self._ck(self.lib.fedmx_precond_set(self.h, 2, 0, 1))
+
+    def ilu0_info(self):
+        """(number of colours, stored blocks, elimination order: node of every permuted row)."""
+        nc, nb = C.c_int(), C.c_int64()
+        order = np.empty(self.n_owned, dtype=np.int32)
+        self._ck(self.lib.fedmx_ilu0_info(self.h, C.byref(nc), C.byref(nb), _np_ptr(order)))
+        return nc.value, nb.value, order
+
+    def ilu0_solve(self, r, z=None):
+        z = self.new_vector() if z is None else z
+        self._ck(self.lib.fedmx_ilu0_solve(self.h, _ptr(r), _ptr(z)))
+        return z
+
     def new_vector(self):
         return torch.zeros(self.n_vertices * self.n_eq, dtype=torch.float64, device=self.device)
 

@@ -68,8 +68,11 @@ class StreamerCase:
             x_lap[:, 2] = U_W * m.coords[:, 1] / BOX
             self.hot.jacobian(torch.from_numpy(x_lap.ravel()).to(self.hot.device), 5e-12, 1e30)
             self.hot.setup_two_stage_preconditioner(2, self.bc_nodes, local_mesh=self.local)
+        elif precond == "ilu0":
+            # the reference test's literal mode: PETSc's default PC for `linear_solver = "gmres"` (fedm_streamer.py:32)
+            self.hot.use_ilu0()
         elif precond != "bjacobi":
-            raise ValueError("precond must be 'amg' or 'bjacobi'")
+            raise ValueError("precond must be 'amg', 'ilu0' or 'bjacobi'")
         self.newton_kw = dict(rtol=newton_rtol, max_it=newton_max_it, ksp_rtol=ksp_rtol, ksp_restart=ksp_restart,
                               ksp_max_it=ksp_max_it)
         dev = self.hot.device
@@ -134,7 +137,7 @@ class StreamerCase:
         pot.set_model(hp.MODEL_POISSON, [ELEMENTARY_CHARGE / EPSILON_0], 2)
         pot.fields.copy_(torch.from_numpy(np.stack([ui, ue], axis=1)))
         phi = pot.new_vector()
-        if self.precond == "amg":
+        if self.precond in ("amg", "ilu0"):                  # the set-up Poisson solve always uses multigrid
             pot.jacobian(phi, 1.0, 1.0)
             pot.setup_two_stage_preconditioner(0, self.bc_nodes, local_mesh=self.local)
         if laplace_guess:

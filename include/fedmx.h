@@ -90,6 +90,15 @@ int fedmx_gps_numbering(int64_t n, const int32_t *h_rowptr, const int32_t *h_col
 int fedmx_dofmap_fenics(fedmx_ctx *ctx, int32_t *h_dof_to_vertex);
 /* dolfin's scalar SparsityPattern in dolfin's own dof numbering (rows/columns n_eq*dof+comp, ascending columns). */
 int fedmx_pattern_get_fenics(fedmx_ctx *ctx, int64_t *n_rows, int64_t *nnz, int64_t *h_rowptr, int32_t *h_colidx);
+/* ILU(0) -- PETSc's default preconditioner behind `linear_solver = "gmres"` of the reference test
+ * (tests/integrated_tests/streamer_discharge/fedm_streamer.py:32,302-305): ILU(0) in serial, block Jacobi + ILU(0) per rank
+ * under mpirun.  One block per GPU (ghost columns dropped), multicolour ordering (fedm_b200/csrc/fedmx_ilu.cu).
+ * fedmx_ilu0_factor: numeric factorisation of the currently assembled Jacobian (symbolic phase on first use);
+ * fedmx_ilu0_solve: z = (LU)^-1 r.  Selected for the Krylov solver with fedmx_precond_set(ctx, 2, 0, 1), after which every
+ * Jacobian assembly refreshes the factors. */
+int fedmx_ilu0_factor(fedmx_ctx *ctx);
+int fedmx_ilu0_solve(fedmx_ctx *ctx, const double *d_r, double *d_z);
+int fedmx_ilu0_info(fedmx_ctx *ctx, int *n_colors, int64_t *n_blocks, int32_t *h_order /* elimination order, may be NULL */);
 /* Copy the assembled Jacobian out as block CSR values [nnz_blocks][n_eq][n_eq] (host buffer). */
 int fedmx_matrix_get_bsr(fedmx_ctx *ctx, double *h_values);
 

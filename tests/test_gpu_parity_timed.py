@@ -162,9 +162,10 @@ def test_partitioned_run_matches_fixture(world):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
-    for mode in ("exact", "bench"):
+    for mode, precond in (("exact", "amg"), ("bench", "amg"), ("bench", "ilu0")):
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-               "--master-port", str(29540 + world), str(ROOT / "tools" / "mgpu_check.py"), "--golden", "--mode", mode]
+               "--master-port", str(29540 + world), str(ROOT / "tools" / "mgpu_check.py"), "--golden", "--mode", mode,
+               "--precond", precond]
         r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
         assert "PASS" in r.stdout

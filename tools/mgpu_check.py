@@ -24,6 +24,7 @@ from fedm_b200.streamer import StreamerCase
 ap = argparse.ArgumentParser()
 ap.add_argument("--golden", action="store_true")
 ap.add_argument("--mode", default="exact", choices=["exact", "bench"])
+ap.add_argument("--precond", default="amg", choices=["amg", "ilu0", "bjacobi"])
 ap.add_argument("--n", type=int, default=32)
 ap.add_argument("--steps", type=int, default=4)
 args = ap.parse_args()
@@ -33,7 +34,7 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 n = 256 if args.golden else args.n
 kw = dict(ksp_rtol=1e-13, ksp_max_it=50000) if args.mode == "exact" else {}
-case = StreamerCase(n=n, device=local, world=world, rank=rank, **kw)
+case = StreamerCase(n=n, device=local, world=world, rank=rank, precond=args.precond, **kw)
 case.set_initial_state()
 if args.golden:
     case.run(T_final=1e-10)
