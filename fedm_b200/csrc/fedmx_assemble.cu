@@ -787,6 +787,19 @@ extern "C" int fedmx_bdf2_history(fedmx_ctx *ctx, int n_hist, const double *d_x_
     return FEDMX_OK;
 }
 
+// plain-vector form of the same history term (used by the 1-D P2 path, fedmx_p2line.cu)
+int fedmx_bdf2_history_raw(fedmx_ctx *ctx, int64_t n, const double *d_x_old, const double *d_x_old1, double dt, double dt_old,
+                           double *d_out) {
+    const double tr = dt / dt_old;
+    const double trp1 = 1.0 + tr;
+    const int threads = 256;
+    bdf2_history_kernel<<<unsigned((n + threads - 1) / threads), threads, 0, ctx->stream>>>(
+        n, 1, 1, d_x_old, d_x_old1, -(trp1 * trp1) / (trp1 * dt), (tr * tr) / (trp1 * dt), d_out, 1, 0);
+    ctx->launches++;
+    FEDMX_CHECK_CUDA(ctx, cudaGetLastError());
+    return FEDMX_OK;
+}
+
 #include <dlfcn.h>
 
 // Load a row kernel generated by the form compiler (fedm_b200/formcompiler.py).  The .so exports

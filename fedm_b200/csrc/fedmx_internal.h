@@ -264,4 +264,6 @@ int fedmx_comm_destroy_internal(fedmx_ctx *ctx);
 int fedmx_ilu0_factor_internal(fedmx_ctx *ctx);
 int fedmx_ilu0_solve_internal(fedmx_ctx *ctx, const double *d_r, double *d_z);
 void fedmx_ilu0_free(fedmx_ctx *ctx);
+int fedmx_bdf2_history_raw(fedmx_ctx *ctx, int64_t n, const double *d_x_old, const double *d_x_old1, double dt, double dt_old,
+                           double *d_out);
 double *fedmx_peer_big_buffer(fedmx_ctx *ctx, int64_t n);

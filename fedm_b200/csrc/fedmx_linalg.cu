@@ -592,7 +592,9 @@ extern "C" int fedmx_spmv(fedmx_ctx *ctx, const double *d_x, double *d_y) {
 
 extern "C" int fedmx_norm2(fedmx_ctx *ctx, const double *d_x, int64_t n, double *out) {
     if (!ctx) return FEDMX_EINVAL;
-    FEDMX_REQUIRE(ctx, ctx->d_red && d_x && out && n >= 0, "fedmx_norm2: bad arguments");
+    FEDMX_REQUIRE(ctx, d_x && out && n >= 0, "fedmx_norm2: bad arguments");
+    int rc;
+    if (!ctx->d_red && (rc = fedmx_ensure_workspace(ctx, 0))) return rc;       // contexts without a triangle mesh (1-D P2 path)
     return fedmx_norm2_local(ctx, d_x, n, out, true);
 }
 

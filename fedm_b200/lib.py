@@ -80,6 +80,9 @@ SIGNATURES = {
     "fedmx_peer_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "fedmx_peer_error": (C.c_int, [C.c_void_p]),
     "fedmx_precond_set": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "fedmx_p2line_assemble": (C.c_int, [C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fedmx_p2line_solve": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fedmx_ilu0_factor": (C.c_int, [C.c_void_p]),
     "fedmx_ilu0_solve": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "fedmx_ilu0_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), c_i64p, C.c_void_p]),

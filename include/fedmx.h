@@ -90,6 +90,16 @@ int fedmx_gps_numbering(int64_t n, const int32_t *h_rowptr, const int32_t *h_col
 int fedmx_dofmap_fenics(fedmx_ctx *ctx, int32_t *h_dof_to_vertex);
 /* dolfin's scalar SparsityPattern in dolfin's own dof numbering (rows/columns n_eq*dof+comp, ascending columns). */
 int fedmx_pattern_get_fenics(fedmx_ctx *ctx, int64_t *n_rows, int64_t *nnz, int64_t *h_rowptr, int32_t *h_colidx);
+/* ---- 1-D P2 elements (BASELINE configs[0]: examples/time_of_flight_1D/fedm-tof_1d.py:87-104) -------------------------------
+ * IntervalMesh + FunctionSpace(mesh, 'P', 2), one log-density unknown, Gamma = -grad(D e^u) + w e^u (fedm-tof_1d.py:114),
+ * balance equation in Cartesian log form (fedm/functions.py:350-368).  dofs in coordinate order (2c, 2c+1, 2c+2 = left vertex,
+ * midpoint, right vertex of cell c).  fedmx_p2line_assemble: BDF2 history into d_hist, residual into d_res and -- if d_band is
+ * not NULL -- the pentadiagonal Jacobian into d_band[ndof][5] (column i-2+k); replaces assemble(F)/assemble(J) behind Problem.F/J.
+ * fedmx_p2line_solve: banded LU without pivoting (the example's direct solver, linear_solver = 'mumps'); destroys band and rhs. */
+int fedmx_p2line_assemble(fedmx_ctx *ctx, int64_t n_cells, double h, double dt, double dt_old, double D, double w,
+                          const double *d_u, const double *d_u_old, const double *d_u_old1, const double *d_f,
+                          double *d_hist, double *d_res, double *d_band);
+int fedmx_p2line_solve(fedmx_ctx *ctx, int64_t ndof, double *d_band, double *d_rhs, double *d_x);
 /* ILU(0) -- PETSc's default preconditioner behind `linear_solver = "gmres"` of the reference test
  * (tests/integrated_tests/streamer_discharge/fedm_streamer.py:32,302-305): ILU(0) in serial, block Jacobi + ILU(0) per rank
  * under mpirun.  One block per GPU (ghost columns dropped), multicolour ordering (fedm_b200/csrc/fedmx_ilu.cu).
