@@ -400,9 +400,22 @@ int fedmx_amg_vcycle(fedmx_ctx *ctx, double *z_out, int z_stride, int z_off) {
     int rc;
     if (ctx->coarse_first < 0 && (rc = setup_coarse_fusion(ctx))) return rc;
     const int cf = ctx->coarse_first;
+    // V(0,1) on the finest level (FEDMX_MG_V01=1; default for partitioned runs whose finest prolongation covers the ghost rows):
+    // no pre-smoothing there, the right-hand side itself is restricted and the prolongated correction is smoothed once.
+    // On a partitioned level this removes BOTH halo exchanges of the cycle (x = P e is evaluated for the ghost rows too, the
+    // coarse correction e being replicated), at the price of a slightly weaker preconditioner.
+    const bool v01 = ctx->amg_v01 && cf > 0 && nu == 1;
     for (int l = 0; l < cf; ++l) {
         ProfScope lprof(ctx, l == 0 ? FEDMX_PROF_MG_FINE : FEDMX_PROF_MG_MID);
         AmgLevel &lv = L[l];
+        if (v01 && l == 0) {
+            constexpr int LPR = 4;
+            const unsigned rb = unsigned((lv.R.n_rows * LPR + 127) / 128);
+            ssell_mult_split_kernel<LPR><<<rb, 128, 0, ctx->stream>>>(lv.R, lv.b, L[1].b);
+            ctx->launches++;
+            if (ctx->n_ranks > 1 && (rc = fedmx_global_sum(ctx, L[1].b, int(L[1].n)))) return rc;
+            continue;
+        }
         const unsigned vb = unsigned((lv.n + 255) / 256);
         const bool fuse_first = nu == 1 && !(l == 0 && ctx->n_ranks > 1);   // distributed level: ghosts of x come by halo exchange
         if (fuse_first) {
@@ -458,9 +471,11 @@ int fedmx_amg_vcycle(fedmx_ctx *ctx, double *z_out, int z_stride, int z_off) {
     for (int l = cf - 1; l >= 0; --l) {
         ProfScope lprof(ctx, l == 0 ? FEDMX_PROF_MG_FINE : FEDMX_PROF_MG_MID);
         AmgLevel &lv = L[l];
-        launch_ssell<MODE_ADD>(ctx, lv.P, L[l + 1].x, nullptr, nullptr, 0.0, lv.x);
+        if (v01 && l == 0) launch_ssell<MODE_MULT>(ctx, lv.P, L[l + 1].x, nullptr, nullptr, 0.0, lv.x);     // x = P e (all local rows)
+        else launch_ssell<MODE_ADD>(ctx, lv.P, L[l + 1].x, nullptr, nullptr, 0.0, lv.x);
         for (int sweep = 0; sweep < nu; ++sweep) {
-            if (l == 0 && ctx->n_ranks > 1 && (rc = fedmx_halo_exchange_internal(ctx, lv.x, 1))) return rc;
+            const bool ghosts_valid = v01 && l == 0 && lv.P.n_rows >= ctx->n_vertices;       // P covers the ghost rows
+            if (l == 0 && ctx->n_ranks > 1 && !ghosts_valid && (rc = fedmx_halo_exchange_internal(ctx, lv.x, 1))) return rc;
             if (l == 0 && sweep == nu - 1) {
                 launch_ssell<MODE_JACOBI_OUT>(ctx, lv.A, lv.x, lv.b, lv.dinv, lv.omega, z_out, z_stride, z_off);
                 break;
@@ -578,6 +593,20 @@ extern "C" int fedmx_amg_add_level(fedmx_ctx *ctx, int64_t n, const double *h_di
     }
     ctx->amg_levels.push_back(lv);
     return FEDMX_OK;
+}
+
+// Partitioned runs: replace the finest level's prolongation by one that also has the rows of the ghost vertices (the coarse
+// correction is replicated, so x = P e can then be formed for the ghosts without a halo exchange) and switch the finest level
+// to the V(0,1) cycle.  n_rows = local vertices incl. ghosts.
+extern "C" int fedmx_amg_set_fine_prolongation(fedmx_ctx *ctx, int64_t n_rows, const int32_t *p_rowptr, const int32_t *p_col,
+                                               const double *p_val, int v01) {
+    if (!ctx) return FEDMX_EINVAL;
+    FEDMX_REQUIRE(ctx, !ctx->amg_levels.empty() && ctx->amg_levels[0].n_coarse > 0, "fedmx_amg_set_fine_prolongation: no hierarchy");
+    ctx->amg_v01 = v01 != 0;
+    if (!p_rowptr) return FEDMX_OK;
+    FEDMX_REQUIRE(ctx, n_rows >= ctx->amg_levels[0].n && n_rows <= ctx->n_vertices, "fedmx_amg_set_fine_prolongation: bad row count");
+    PoolScope pool(ctx, &ctx->amg_device);
+    return upload_ssell(ctx, ctx->amg_levels[0].P, n_rows, ctx->amg_levels[0].n_coarse, p_rowptr, p_col, p_val);
 }
 
 extern "C" int fedmx_amg_set_coarse(fedmx_ctx *ctx, int n, const double *h_inverse) {

@@ -1,7 +1,17 @@
 // Context life cycle, error reporting, host-side step-size controllers.
 #include <math.h>
 
+#include <nvtx3/nvToolsExt.h>
+#include <stdlib.h>
+
 #include "fedmx_internal.h"
+
+// FEDMX_NVTX=1: every profiled kernel class is also an NVTX range on the calling thread (visible in Nsight Systems / ncu
+// --nvtx; the reference has no tracing of its own).  Header-only NVTX v3: no extra library.
+static const bool g_nvtx = getenv("FEDMX_NVTX") && atoi(getenv("FEDMX_NVTX")) != 0;
+static const char *const kProfNames[FEDMX_PROF_KINDS] = {"fedmx:assemble_jacobian", "fedmx:assemble_residual", "fedmx:spmv",
+                                                         "fedmx:orthogonalisation", "fedmx:preconditioner", "fedmx:mg_fine",
+                                                         "fedmx:mg_mid", "fedmx:mg_coarse", "fedmx:comm"};
 
 extern "C" const char *fedmx_version(void) { return "fedmx 0.1 (sm_100a)"; }
 
@@ -53,6 +63,7 @@ extern "C" int64_t fedmx_launch_count(fedmx_ctx *ctx, int reset) {
 
 // ---- profiling -----------------------------------------------------------------------------------------
 ProfScope::ProfScope(fedmx_ctx *ctx, int k) : c(ctx), kind(k) {
+    if (g_nvtx) nvtxRangePushA(kProfNames[k]);
     if (!c->prof_on || (k >= FEDMX_PROF_MG_FINE && c->prof_on < 2)) return;
     auto &pool = c->prof_ev[kind];
     if (c->prof_used[kind] + 2 > pool.size()) {
@@ -65,6 +76,7 @@ ProfScope::ProfScope(fedmx_ctx *ctx, int k) : c(ctx), kind(k) {
     cudaEventRecord(start, c->stream);
 }
 ProfScope::~ProfScope() {
+    if (g_nvtx) nvtxRangePop();
     if (stop) { cudaEventRecord(stop, c->stream); c->prof_count[kind]++; }
 }
 int fedmx_profile_flush(fedmx_ctx *ctx, int kind) {

@@ -175,6 +175,7 @@ struct fedmx_ctx {
     IluPlan *ilu = nullptr;
     int newton_expected_its = 0;   // Newton iterations of the previous converged solve (predictor for speculative J assembly)
     int precond_kind = 0, amg_comp = 0, amg_nu = 1;
+    bool amg_v01 = false;            // finest multigrid level runs a V(0,1) cycle (see fedmx_amg_vcycle)
     std::vector<AmgLevel> amg_levels;
     double *amg_coarse_inv = nullptr;
     double *d_tmp = nullptr;

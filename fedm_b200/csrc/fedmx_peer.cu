@@ -22,14 +22,20 @@
 //  * big allreduce (restricted multigrid residual): barrier, then rank r pulls chunk r of every peer's input, sums in
 //    rank order and pushes the chunk into every peer's output; flags; copy out.
 // Every spin loop has a clock64() timeout that raises an error flag instead of hanging the GPU.
+#include <stdlib.h>
 #include <string.h>
+
+#include <algorithm>
 
 #include "fedmx_internal.h"
 
 namespace {
 
 constexpr int kArMax = FEDMX_PEER_AR_MAX;
-constexpr long long kSpinTimeout = 6000000000LL;     // ~3 s at 2 GHz
+// Spin time-out in SM clocks.  Ordinary rank skew (host-side multigrid set-up, JIT compilation, rank-0 output) can be many
+// seconds, so the default is generous (FEDMX_PEER_TIMEOUT_S, default 120 s); a time-out is FATAL for the run -- the flag is
+// sticky and every later library call on the context fails (ranks must not continue on diverging control flow).
+__device__ long long g_spin_timeout = 240000000000LL;
 
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -42,7 +48,7 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 __device__ __forceinline__ bool spin_until(const unsigned long long *flag, unsigned long long epoch, int *err) {
     const long long t0 = clock64();
     while (ld_acquire_sys(flag) < epoch) {
-        if (clock64() - t0 > kSpinTimeout) { *err = 1; return false; }
+        if (clock64() - t0 > g_spin_timeout) { *err = 1; return false; }
     }
     return true;
 }
@@ -218,6 +224,12 @@ extern "C" int fedmx_peer_create(fedmx_ctx *ctx, int64_t halo_capacity, int64_t 
     FEDMX_CHECK_CUDA(ctx, cudaMemcpy(P.base + P.off_flags + size_t(3) * R * sizeof(unsigned long long), &probe, sizeof(probe), cudaMemcpyHostToDevice));
     FEDMX_CHECK_CUDA(ctx, cudaMalloc((void **)&P.d_counter, 2 * sizeof(unsigned int)));
     FEDMX_CHECK_CUDA(ctx, cudaMemset(P.d_counter, 0, 2 * sizeof(unsigned int)));
+    {
+        const char *env = getenv("FEDMX_PEER_TIMEOUT_S");
+        const double secs = env ? atof(env) : 120.0;
+        const long long clocks = (long long)(std::max(1.0, secs) * 2.0e9);
+        FEDMX_CHECK_CUDA(ctx, cudaMemcpyToSymbol(g_spin_timeout, &clocks, sizeof(clocks)));
+    }
     FEDMX_CHECK_CUDA(ctx, cudaHostAlloc((void **)&P.h_err, sizeof(int), cudaHostAllocMapped));
     *P.h_err = 0;
     FEDMX_CHECK_CUDA(ctx, cudaHostGetDevicePointer((void **)&P.d_err, P.h_err, 0));

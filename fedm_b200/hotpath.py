@@ -184,6 +184,17 @@ class HotPath:
                                                       None, None, None, 0, None, None, None, None, None, None))
         ci = f64(coarse_inv)
         self._ck(self.lib.fedmx_amg_set_coarse(self.h, ci.shape[0], _np_ptr(ci)))
+        # finest-level cycle: V(1,1) on one GPU; partitioned runs default to V(0,1) with a prolongation that covers the ghost
+        # rows, which removes both halo exchanges of the cycle (FEDMX_MG_V01=0/1 overrides)
+        v01 = os.environ.get("FEDMX_MG_V01")
+        v01 = (fine_ops is not None) if v01 is None else v01 == "1"
+        if v01 and len(levels) > 1:
+            if fine_ops is not None:
+                Pg = levels[0]["P"][local_mesh.local_to_global].tocsr()            # owned + ghost rows, coarse ids are global
+                self._ck(self.lib.fedmx_amg_set_fine_prolongation(self.h, Pg.shape[0], _np_ptr(i32(Pg.indptr)), _np_ptr(i32(Pg.indices)),
+                                                                  _np_ptr(f64(Pg.data)), 1))
+            else:
+                self._ck(self.lib.fedmx_amg_set_fine_prolongation(self.h, 0, None, None, None, 1))
         self._ck(self.lib.fedmx_precond_set(self.h, 1, comp, nu))
         self.amg_levels = [lv["A"].shape[0] for lv in levels]
         self.amg_host = (levels, coarse_inv)             # kept for tests (numpy reference cycle)
@@ -326,8 +337,25 @@ class HotPath:
 
     def peer_init(self, world, rank, neighbor_ranks, recv_ptr, n_global_vertices):
         """NVLink peer-memory transport (fedmx_peer.cu): allocate the symmetric heap, exchange the CUDA IPC handles and the
-        per-neighbour staging offsets over torch.distributed, map every peer.  Call after comm_init + set_halo."""
+        per-neighbour staging offsets over torch.distributed, map every peer.  Call after comm_init + set_halo.
+        Every stage that can fail locally (allocation, IPC open) is followed by a collective agreement, so either ALL ranks end
+        up on the peer transport or all stay on NCCL -- no rank is left waiting in a collective the others skipped.
+        Returns True when the peer transport is active."""
         import torch.distributed as dist
+
+        def agree(ok):
+            t = torch.tensor([1 if ok else 0], device=self.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            return bool(t.item())
+
+        def stage(fn):
+            try:
+                fn()
+                return True
+            except Exception as exc:                           # e.g. CUDA IPC not permitted in this container
+                print(f"[fedm_b200] rank {rank}: peer-memory transport unavailable ({exc})", flush=True)
+                return False
+
         nb = [int(q) for q in neighbor_ranks]
         rp = [int(v) for v in recv_ptr]
         plans = [None] * world
@@ -335,14 +363,25 @@ class HotPath:
         halo_cap = 5 * max(p[1][-1] for p in plans) + 64          # FEDMX_MAX_EQ components per ghost node
         big_cap = int(n_global_vertices) // 2 + 1024              # restricted multigrid residual (level 1 of the hierarchy)
         handle = C.create_string_buffer(64)
-        self._ck(self.lib.fedmx_peer_create(self.h, halo_cap, big_cap, handle))
+        created = stage(lambda: self._ck(self.lib.fedmx_peer_create(self.h, halo_cap, big_cap, handle)))
+        if not agree(created):
+            if created:
+                self.peer_enable(False)
+            return False
         handles = [None] * world
         dist.all_gather_object(handles, handle.raw)
-        self._ck(self.lib.fedmx_peer_open(self.h, b"".join(handles)))
+        opened = stage(lambda: self._ck(self.lib.fedmx_peer_open(self.h, b"".join(handles))))
+        if not agree(opened):
+            self.peer_enable(False)
+            return False
         from .partition import peer_staging_offsets
         remote = np.array(peer_staging_offsets(rank, plans), dtype=np.int32)
-        self._ck(self.lib.fedmx_peer_halo_set(self.h, len(nb), _np_ptr(remote)))
+        ready = stage(lambda: self._ck(self.lib.fedmx_peer_halo_set(self.h, len(nb), _np_ptr(remote))))
+        if not agree(ready):
+            self.peer_enable(False)
+            return False
         dist.barrier()
+        return True
 
     def peer_enable(self, on=True):
         self._ck(self.lib.fedmx_peer_enable(self.h, 1 if on else 0))

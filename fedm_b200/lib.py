@@ -90,6 +90,7 @@ SIGNATURES = {
     "fedmx_amg_add_level": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fedmx_amg_set_coarse": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "fedmx_amg_set_fine_prolongation": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "fedmx_matrix_get_component": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "fedmx_launch_count": (C.c_int64, [C.c_void_p, C.c_int]),
     "fedmx_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),

@@ -105,17 +105,8 @@ class StreamerCase:
         # fedmx_peer.cu (measured on 2/4/8 B200: the same step time within 2 % -- NCCL's LL/NVLS paths are already at the NVLink
         # latency floor for these message sizes -- so the battle-tested transport is the default)
         if os.environ.get("FEDMX_PEER", "0") == "1":
-            try:
-                hot.peer_init(self.world, self.rank, lm.neighbors, lm.recv_ptr, lm.n_global_vertices)
-                ok = 1
-            except Exception as exc:                       # e.g. CUDA IPC not permitted in this container: stay on NCCL
-                print(f"[fedm_b200] rank {self.rank}: peer-memory transport unavailable ({exc}); using NCCL", flush=True)
-                ok = 0
-            import torch.distributed as dist
-            flag = torch.tensor([ok], device=hot.device)
-            dist.all_reduce(flag, op=dist.ReduceOp.MIN)    # all ranks must agree on the transport
-            if not int(flag.item()) and ok:
-                hot.peer_enable(False)
+            if not hot.peer_init(self.world, self.rank, lm.neighbors, lm.recv_ptr, lm.n_global_vertices) and self.rank == 0:
+                print("[fedm_b200] peer-memory transport not available on every rank: all ranks use NCCL", flush=True)
 
     # ---- initial condition + initial Poisson solve ---------------------------------------------------
     def initial_log_densities(self):

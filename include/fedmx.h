@@ -174,6 +174,11 @@ int fedmx_amg_add_level(fedmx_ctx *ctx, int64_t n, const double *h_dinv, double 
                         const int32_t *a_rowptr, const int32_t *a_col, const double *a_val, int64_t n_coarse,
                         const int32_t *p_rowptr, const int32_t *p_col, const double *p_val,
                         const int32_t *r_rowptr, const int32_t *r_col, const double *r_val);
+/* Finest-level options of the multigrid stage: v01 != 0 selects a V(0,1) cycle there (restrict the right-hand side, smooth the
+ * prolongated correction once); with a prolongation that also holds the rows of the ghost vertices (n_rows = local vertices)
+ * a partitioned V-cycle then needs no halo exchange at all, only the allreduce of the restricted right-hand side. */
+int fedmx_amg_set_fine_prolongation(fedmx_ctx *ctx, int64_t n_rows, const int32_t *p_rowptr, const int32_t *p_col,
+                                    const double *p_val, int v01);
 int fedmx_amg_set_coarse(fedmx_ctx *ctx, int n, const double *h_inverse);
 int fedmx_matrix_get_component(fedmx_ctx *ctx, int i, int j, double *h_values);
 

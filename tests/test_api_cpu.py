@@ -183,3 +183,24 @@ def test_segregated_helpers_on_numpy_backend():
     finally:
         df.set_backend(None)
     check_helpers(out)
+
+
+def test_marking_circle_boundaries():
+    """'circle' entries of Marking_boundaries (fedm/functions.py:48-70, 95-98): facets whose vertices and midpoint lie on the
+    arc (within the reference's tolerance 1e-8 on the squared distance) and outside the gap are marked; works on the same
+    marker function that feeds the device path's `ds(i)` measures."""
+    from fedm_b200 import dolfin as df
+    from fedm_b200.mesh import TriMesh, rectangle
+    m = rectangle((0.0, 0.0), (4e-4, 4e-4), 40, 40, "right")
+    R, cz = 1e-3, -1e-3 + 0.0                                   # needle-like electrode: arc through (r=0, z=0), centre below
+    xy = m.coords.copy()
+    bottom = np.abs(xy[:, 1]) < 1e-15
+    # bend the bottom edge onto the circle of radius R around (r=0, z=cz): z = cz + sqrt(R^2 - r^2) <= 0
+    xy[bottom, 1] = cz + np.sqrt(R ** 2 - xy[bottom, 0] ** 2)
+    mesh = df.Mesh(TriMesh(xy, m.cells))
+    markers = F.Marking_boundaries(mesh, [["circle", cz, 0.0, R], ["line", 4e-4, 4e-4, 0.0, 4e-4]], gap_length=4e-4)
+    vals = np.asarray(markers.array())
+    fv = markers.facets if hasattr(markers, "facets") else mesh.tri.exterior_facets()
+    on_arc = [i for i, (a, b) in enumerate(fv) if bottom[a] and bottom[b]]
+    assert len(on_arc) == 40 and all(vals[i] == 1 for i in on_arc)
+    assert (vals == 2).sum() == 40 and (vals == 1).sum() == 40
