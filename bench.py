@@ -34,30 +34,64 @@ def peaks():
 
 
 class ClockSampler:
+    """SM clock and throttle reasons DURING the timed region: NVML polled every 10 ms from a thread of this process (the
+    timed region of a multi-GPU run lasts a few hundred ms -- too short for a freshly spawned `nvidia-smi -lms` to report);
+    falls back to `nvidia-smi` if the NVML binding is missing."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
-        self.lines, self.proc, self.index = [], None, index
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self.stop_flag, self.th, self.proc, self.lines = False, None, None, []
+
+    def _poll(self):
+        import pynvml as nv
+        h = None
+        try:                                               # the CUDA ordinal may differ from NVML's (CUDA_VISIBLE_DEVICES): use the UUID
+            import torch
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            h = nv.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        except Exception:
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+        while not self.stop_flag:
+            self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+            r = int(get_reasons(h))
+            for name, bit in bits.items():
+                if r & bit:
+                    self.reasons.add(name)
+            time.sleep(0.01)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
+            import pynvml as nv
+            nv.nvmlInit()
+            self.th = threading.Thread(target=self._poll, daemon=True)
             self.th.start()
+            return
+        except Exception:
+            self.th = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.rd = threading.Thread(target=lambda: [self.lines.append(ln.strip()) for ln in self.proc.stdout], daemon=True)
+            self.rd.start()
         except Exception:
             self.proc = None
 
-    def _read(self):
-        for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
-
     def stop(self):
+        if self.th is not None:
+            self.stop_flag = True
+            self.th.join(timeout=1.0)
+            sm = sorted(self.samples)
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                    "samples": len(sm), "source": "NVML, 10 ms period, timed region only"}
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"], "samples": 0}
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -79,7 +113,7 @@ class ClockSampler:
                     reasons.add(nm)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi -lms 50"}
 
 
 def algorithmic_bytes(nv, nc, n_eq=3, zero_entries=1):

@@ -281,12 +281,16 @@ inline bool launch_tiled(const AsmArgs &A, const TileView &T, bool jac, cudaStre
     const size_t bytes = jac ? tiled_smem_bytes<Model, true>(P.vtx_cap, P.cell_cap) : tiled_smem_bytes<Model, false>(P.vtx_cap, P.cell_cap);
     if (bytes > 200 * 1024) return false;
     static bool attr_set = false;
+    // FEDMX_TILED_MINB=2: the Jacobian kernel compiled for 2 instead of 3 resident CTAs per SM (255 registers, no spills) -- tuning knob
+    static const bool minb2 = getenv("FEDMX_TILED_MINB") && atoi(getenv("FEDMX_TILED_MINB")) == 2;
     if (!attr_set) {
         cudaFuncSetAttribute(assemble_tiled_kernel<Model, true, Model::TILED_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(assemble_tiled_kernel<Model, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         cudaFuncSetAttribute(assemble_tiled_kernel<Model, false, Model::TILED_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set = true;
     }
-    if (jac) assemble_tiled_kernel<Model, true, Model::TILED_MINB><<<unsigned(T.n_tiles), FEDMX_TILE, bytes, stream>>>(P);
+    if (jac && minb2) assemble_tiled_kernel<Model, true, 2><<<unsigned(T.n_tiles), FEDMX_TILE, bytes, stream>>>(P);
+    else if (jac) assemble_tiled_kernel<Model, true, Model::TILED_MINB><<<unsigned(T.n_tiles), FEDMX_TILE, bytes, stream>>>(P);
     else assemble_tiled_kernel<Model, false, Model::TILED_MINB><<<unsigned(T.n_tiles), FEDMX_TILE, bytes, stream>>>(P);
     return true;
 }
