@@ -405,7 +405,11 @@ int fedmx_amg_vcycle(fedmx_ctx *ctx, double *z_out, int z_stride, int z_off) {
     // On a partitioned level this removes BOTH halo exchanges of the cycle (x = P e is evaluated for the ghost rows too, the
     // coarse correction e being replicated), at the price of a slightly weaker preconditioner.
     const bool v01 = ctx->amg_v01 && cf > 0 && nu == 1;
-    for (int l = 0; l < cf; ++l) {
+    // ---- the levels below the finest are replicated on every rank and need no communication: their ~15 small kernels (6-9 us
+    // each, launch-latency bound) are captured once into a CUDA graph and replayed.  The smoothers ping-pong x/x2, so the
+    // kernel arguments alternate with period two: one graph per parity.
+    static const bool env_graph = !(getenv("FEDMX_MG_GRAPH") && atoi(getenv("FEDMX_MG_GRAPH")) == 0);
+    auto down_level = [&](int l) -> int {
         ProfScope lprof(ctx, l == 0 ? FEDMX_PROF_MG_FINE : FEDMX_PROF_MG_MID);
         AmgLevel &lv = L[l];
         if (v01 && l == 0) {
@@ -414,7 +418,7 @@ int fedmx_amg_vcycle(fedmx_ctx *ctx, double *z_out, int z_stride, int z_off) {
             ssell_mult_split_kernel<LPR><<<rb, 128, 0, ctx->stream>>>(lv.R, lv.b, L[1].b);
             ctx->launches++;
             if (ctx->n_ranks > 1 && (rc = fedmx_global_sum(ctx, L[1].b, int(L[1].n)))) return rc;
-            continue;
+            return FEDMX_OK;
         }
         const unsigned vb = unsigned((lv.n + 255) / 256);
         const bool fuse_first = nu == 1 && !(l == 0 && ctx->n_ranks > 1);   // distributed level: ghosts of x come by halo exchange
@@ -440,35 +444,37 @@ int fedmx_amg_vcycle(fedmx_ctx *ctx, double *z_out, int z_stride, int z_off) {
         }
         // distributed fine level: R holds only this rank's fine columns; the coarse right-hand side is the sum over ranks
         if (dist && (rc = fedmx_global_sum(ctx, L[l + 1].b, int(L[l + 1].n)))) return rc;
-    }
-    if (ctx->coarse_grid_blocks > 0) {
+        return FEDMX_OK;
+    };
+    auto coarse_levels = [&]() -> int {
         ProfScope cprof(ctx, FEDMX_PROF_MG_COARSE);
-        const CoarseLevelDev *levels = (const CoarseLevelDev *)ctx->d_coarse_levels;
-        int count = ctx->coarse_count, sweeps = nu;
-        const double *cinv = ctx->amg_coarse_inv;
-        unsigned int *bstate = ctx->d_grid_barrier;
-        void *args[] = {(void *)&levels, (void *)&count, (void *)&sweeps, (void *)&cinv, (void *)&bstate};
-        FEDMX_CHECK_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)coarse_vcycle_grid_kernel, dim3(ctx->coarse_grid_blocks),
-                                                          dim3(512), args, 0, ctx->stream));
+        if (ctx->coarse_grid_blocks > 0) {
+            const CoarseLevelDev *levels = (const CoarseLevelDev *)ctx->d_coarse_levels;
+            int count = ctx->coarse_count, sweeps = nu;
+            const double *cinv = ctx->amg_coarse_inv;
+            unsigned int *bstate = ctx->d_grid_barrier;
+            void *args[] = {(void *)&levels, (void *)&count, (void *)&sweeps, (void *)&cinv, (void *)&bstate};
+            FEDMX_CHECK_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)coarse_vcycle_grid_kernel, dim3(ctx->coarse_grid_blocks),
+                                                              dim3(512), args, 0, ctx->stream));
+        } else {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(kClusterSize);
+            cfg.blockDim = dim3(1024);
+            cfg.stream = ctx->stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = kClusterSize;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            FEDMX_CHECK_CUDA(ctx, cudaLaunchKernelEx(&cfg, coarse_vcycle_kernel, (const CoarseLevelDev *)ctx->d_coarse_levels,
+                                                     ctx->coarse_count, nu, (const double *)ctx->amg_coarse_inv));
+        }
         ctx->launches++;
-    } else {
-        ProfScope cprof(ctx, FEDMX_PROF_MG_COARSE);
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(kClusterSize);
-        cfg.blockDim = dim3(1024);
-        cfg.stream = ctx->stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = kClusterSize;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        FEDMX_CHECK_CUDA(ctx, cudaLaunchKernelEx(&cfg, coarse_vcycle_kernel, (const CoarseLevelDev *)ctx->d_coarse_levels,
-                                                 ctx->coarse_count, nu, (const double *)ctx->amg_coarse_inv));
-        ctx->launches++;
-    }
-    for (int l = cf - 1; l >= 0; --l) {
+        return FEDMX_OK;
+    };
+    auto up_level = [&](int l) -> int {
         ProfScope lprof(ctx, l == 0 ? FEDMX_PROF_MG_FINE : FEDMX_PROF_MG_MID);
         AmgLevel &lv = L[l];
         if (v01 && l == 0) launch_ssell<MODE_MULT>(ctx, lv.P, L[l + 1].x, nullptr, nullptr, 0.0, lv.x);     // x = P e (all local rows)
@@ -483,7 +489,43 @@ int fedmx_amg_vcycle(fedmx_ctx *ctx, double *z_out, int z_stride, int z_off) {
             launch_ssell<MODE_JACOBI>(ctx, lv.A, lv.x, lv.b, lv.dinv, lv.omega, lv.x2);
             std::swap(lv.x, lv.x2);
         }
+        return FEDMX_OK;
+    };
+    auto replicated_section = [&]() -> int {               // levels 1 .. cf-1 down, fused coarse levels, levels cf-1 .. 1 up
+        for (int l = 1; l < cf; ++l)
+            if ((rc = down_level(l))) return rc;
+        if ((rc = coarse_levels())) return rc;
+        for (int l = cf - 1; l >= 1; --l)
+            if ((rc = up_level(l))) return rc;
+        return FEDMX_OK;
+    };
+    if (cf >= 1 && (rc = down_level(0))) return rc;
+    const bool use_graph = env_graph && cf >= 2 && nu == 1 && ctx->prof_on < 2 && ctx->coarse_grid_blocks == 0 && ctx->stream != 0;
+    if (cf == 0) {
+        if ((rc = coarse_levels())) return rc;
+    } else if (!use_graph) {
+        if ((rc = replicated_section())) return rc;
+    } else {
+        cudaGraphExec_t &exec = ctx->mg_graph[ctx->mg_parity];
+        if (!exec) {
+            const int64_t before = ctx->launches;
+            cudaGraph_t graph = nullptr;
+            FEDMX_CHECK_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+            rc = replicated_section();                     // recorded, not executed; performs this cycle's x/x2 swaps
+            cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+            if (rc) return rc;
+            FEDMX_CHECK_CUDA(ctx, ce);
+            FEDMX_CHECK_CUDA(ctx, cudaGraphInstantiate(&exec, graph, 0));
+            cudaGraphDestroy(graph);
+            ctx->mg_graph_nodes = int(ctx->launches - before);
+        } else {
+            for (int l = 1; l < cf; ++l) std::swap(L[l].x, L[l].x2);      // what the section does on the host
+            ctx->launches += ctx->mg_graph_nodes;
+        }
+        FEDMX_CHECK_CUDA(ctx, cudaGraphLaunch(exec, ctx->stream));
+        ctx->mg_parity ^= 1;
     }
+    if (cf >= 1 && (rc = up_level(0))) return rc;
     if (cf == 0) {                                          // the whole hierarchy ran inside the fused kernel
         const int64_t n = L[0].n;
         comp_scatter_kernel<<<unsigned((n + 255) / 256), 256, 0, ctx->stream>>>(L[0].x, z_out, z_stride, z_off, n);
@@ -546,6 +588,8 @@ extern "C" int fedmx_amg_reset(fedmx_ctx *ctx) {
     for (void *p : ctx->amg_device) cudaFree(p);      // a second set-up (new mesh marks, new block) must not leak the first
     ctx->amg_device.clear();
     ctx->amg_levels.clear();
+    for (auto &g : ctx->mg_graph) { if (g) cudaGraphExecDestroy(g); g = nullptr; }
+    ctx->mg_parity = 0;
     ctx->amg_coarse_inv = nullptr;
     ctx->d_coarse_levels = nullptr;
     ctx->d_grid_barrier = nullptr;
@@ -630,6 +674,8 @@ extern "C" int fedmx_precond_set(fedmx_ctx *ctx, int kind, int comp, int nu) {
     ctx->amg_comp = comp;
     ctx->amg_nu = nu;
     ctx->coarse_first = -1;
+    for (auto &g : ctx->mg_graph) { if (g) cudaGraphExecDestroy(g); g = nullptr; }
+    ctx->mg_parity = 0;
     if (kind == 2 && ctx->d_val) return fedmx_ilu0_factor_internal(ctx);     // factor the matrix that is assembled right now
     return FEDMX_OK;
 }

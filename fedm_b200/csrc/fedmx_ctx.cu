@@ -26,6 +26,10 @@ extern "C" int fedmx_ctx_create(int device, fedmx_ctx **out) {
     ctx->device = device;
     ctx->mp = ModelParams{};
     ctx->mp.bc_comp = -1;
+    // The library runs on its own BLOCKING stream: it keeps the implicit ordering with work the caller queues on the legacy
+    // default stream (torch's copies between solves) and, unlike the legacy stream itself, can be captured into CUDA graphs.
+    if (cudaStreamCreate(&ctx->stream) == cudaSuccess) ctx->own_stream = true;
+    else ctx->stream = 0;
     *out = ctx;
     return FEDMX_OK;
 }
@@ -37,6 +41,9 @@ extern "C" int fedmx_ctx_destroy(fedmx_ctx *ctx) {
     fedmx_peer_destroy(ctx);
     fedmx_comm_destroy_internal(ctx);
     fedmx_ilu0_free(ctx);
+    for (auto &g : ctx->mg_graph)
+        if (g) cudaGraphExecDestroy(g);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     for (void *p : ctx->owned_device) cudaFree(p);
     for (void *p : ctx->amg_device) cudaFree(p);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
@@ -50,6 +57,7 @@ extern "C" const char *fedmx_last_error(const fedmx_ctx *ctx) { return ctx ? ctx
 
 extern "C" int fedmx_set_stream(fedmx_ctx *ctx, void *cuda_stream) {
     if (!ctx) return FEDMX_EINVAL;
+    if (ctx->own_stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); ctx->own_stream = false; }
     ctx->stream = (cudaStream_t)cuda_stream;
     return FEDMX_OK;
 }

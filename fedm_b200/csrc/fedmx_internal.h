@@ -132,6 +132,7 @@ struct IluPlan;
 struct fedmx_ctx {
     int device = 0;
     cudaStream_t stream = 0;
+    bool own_stream = false;
     std::string err;
     int64_t launches = 0;
 
@@ -175,6 +176,8 @@ struct fedmx_ctx {
     IluPlan *ilu = nullptr;
     int newton_expected_its = 0;   // Newton iterations of the previous converged solve (predictor for speculative J assembly)
     int precond_kind = 0, amg_comp = 0, amg_nu = 1;
+    cudaGraphExec_t mg_graph[2] = {nullptr, nullptr};   // replicated multigrid levels, one graph per x/x2 ping-pong parity
+    int mg_parity = 0, mg_graph_nodes = 0;
     bool amg_v01 = false;            // finest multigrid level runs a V(0,1) cycle (see fedmx_amg_vcycle)
     std::vector<AmgLevel> amg_levels;
     double *amg_coarse_inv = nullptr;

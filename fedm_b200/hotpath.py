@@ -111,7 +111,7 @@ class HotPath:
         self._ck(self.lib.fedmx_matrix_get_component(self.h, i, j, _np_ptr(vals)))
         return sp.csr_matrix((vals, colidx, rowptr), shape=(self.n_owned, self.n_vertices))
 
-    def setup_two_stage_preconditioner(self, comp, bc_nodes, nu=1, theta=0.0, local_mesh=None):
+    def setup_two_stage_preconditioner(self, comp, bc_nodes, nu=1, theta=0.0, local_mesh=None, hierarchy=None):
         """Builds the smoothed-aggregation hierarchy of the (state-independent) comp-comp block of the Jacobian that
         is currently assembled on the device, uploads it and switches GMRES to the two-stage preconditioner.
         Partitioned runs (local_mesh given): the owned rows of all ranks are gathered into the global block, every
@@ -121,14 +121,29 @@ class HotPath:
         import scipy.sparse as sp
         from . import amg
         nu = int(os.environ.get("FEDMX_AMG_NU", nu))
-        Kloc = self.matrix_component(comp, comp)
+        # hierarchy=(levels, coarse_inv): re-use the host hierarchy of another context with the SAME operator on the same mesh
+        # (e.g. the set-up Poisson problem and the potential block of the coupled system: both are 2 pi r grad u . grad v)
+        Kloc = self.matrix_component(comp, comp) if hierarchy is None else None
         bc = np.asarray(bc_nodes, dtype=np.int64)
         i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
         f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
         if local_mesh is None or local_mesh.world == 1:
-            K = amg.symmetric_dirichlet(Kloc[:, :self.n_owned], bc[bc < self.n_owned])
-            levels, coarse_inv = amg.build_hierarchy(K, theta=theta, coarse_size=int(os.environ.get('FEDMX_AMG_COARSE', 600)))
+            if hierarchy is None:
+                K = amg.symmetric_dirichlet(Kloc[:, :self.n_owned], bc[bc < self.n_owned])
+                levels, coarse_inv = amg.build_hierarchy(K, theta=theta, coarse_size=int(os.environ.get('FEDMX_AMG_COARSE', 600)))
+            else:
+                levels, coarse_inv = hierarchy
             fine_ops = None
+        elif hierarchy is not None:
+            lm = local_mesh
+            l2g = lm.local_to_global
+            levels, coarse_inv = hierarchy
+            owned_g = l2g[:self.n_owned]
+            g2l = lm.global_to_local()
+            A0 = levels[0]["A"][owned_g].tocsr()
+            A0 = sp.csr_matrix((A0.data, g2l[A0.indices], A0.indptr), shape=(self.n_owned, self.n_vertices))
+            fine_ops = (A0, levels[0]["P"][owned_g].tocsr(), levels[0]["R"][:, owned_g].tocsr(), levels[0]["dinv"][owned_g],
+                        levels[0]["A"].diagonal()[owned_g], np.diff(levels[0]["A"].indptr)[owned_g] == 1)
         else:
             import torch.distributed as dist
             lm = local_mesh

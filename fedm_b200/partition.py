@@ -99,15 +99,25 @@ def build_local_mesh(coords, cells, facet_vertices, facet_markers, owner, rank, 
     recv_by = {}
     for q in np.unique(owner[ghosts]):
         recv_by[int(q)] = ghosts[owner[ghosts] == q]                      # ascending global id
+    # my owned nodes that are ghosts on rank q = my vertices of the cells that also have a vertex owned by q (one pass over
+    # the cells of mixed ownership instead of one pass per rank)
     send_by = {}
-    for q in range(world):
-        if q == rank:
-            continue
-        touch_q = (owner[cells] == q).any(axis=1)
-        vq = np.unique(cells[touch_q])
-        mine = vq[owner[vq] == rank]
-        if mine.size:
-            send_by[q] = mine                                             # ascending global id == q's recv order
+    oc = owner[lcells_g]                                                   # cells touching my vertices are the only candidates
+    mixed = (oc != oc[:, :1]).any(axis=1)
+    if mixed.any():
+        cm, om = lcells_g[mixed], oc[mixed]
+        pairs = []
+        for a in range(3):
+            for b in range(3):
+                if a == b:
+                    continue
+                sel = (om[:, a] == rank) & (om[:, b] != rank)
+                if sel.any():
+                    pairs.append(np.stack([om[sel, b].astype(np.int64), cm[sel, a].astype(np.int64)], axis=1))
+        if pairs:
+            pr = np.unique(np.concatenate(pairs), axis=0)                  # sorted by (rank, node): ascending global id per rank
+            for q in np.unique(pr[:, 0]):
+                send_by[int(q)] = pr[pr[:, 0] == q, 1]
     neighbors = sorted(set(recv_by) | set(send_by))
     send_ptr, recv_ptr, send_nodes, recv_nodes = [0], [0], [], []
     for q in neighbors:

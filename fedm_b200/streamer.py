@@ -130,7 +130,10 @@ class StreamerCase:
         phi = pot.new_vector()
         if self.precond in ("amg", "ilu0"):                  # the set-up Poisson solve always uses multigrid
             pot.jacobian(phi, 1.0, 1.0)
-            pot.setup_two_stage_preconditioner(0, self.bc_nodes, local_mesh=self.local)
+            # same operator (2 pi r grad u . grad v with the same Dirichlet rows) as the potential block of the coupled system:
+            # re-use its host hierarchy instead of building it a second time
+            pot.setup_two_stage_preconditioner(0, self.bc_nodes, local_mesh=self.local,
+                                               hierarchy=getattr(self.hot, "amg_host", None) if self.precond == "amg" else None)
         if laplace_guess:
             phi.copy_(torch.from_numpy(U_W * m.coords[:, 1] / BOX))
         res = pot.newton(phi, 1.0, 1.0, rtol=1e-12, atol=0.0, max_it=5 if not laplace_guess else 1, ksp_rtol=ksp_rtol,
