@@ -881,6 +881,9 @@ class File:
         t = 0.0
         if isinstance(obj, tuple):
             obj, t = obj
+        if MPI.rank() != 0:                       # vectors are replicated on every rank: rank 0 writes (dolfin does collective IO)
+            self.count += isinstance(obj, Function)
+            return self
         self.path.parent.mkdir(parents=True, exist_ok=True)
         if not isinstance(obj, Function):
             return self                           # meshes and mesh functions: not needed downstream
@@ -940,6 +943,8 @@ class XDMFFile:
         space = f.function_space()
         if space.n_comp != 1:
             raise ValueError("XDMFFile.write_checkpoint: scalar P1 functions only (FEDM writes one file per species)")
+        if MPI.rank() != 0:                       # replicated vectors: rank 0 writes the (serial-layout) checkpoint
+            return
         tri = space.mesh().tri
         key = (id(tri.cells), tri.num_vertices)
         if key not in self._v2d:

@@ -339,9 +339,10 @@ def adaptive_solver(nonlinear_solver, problem, t, dt, dt_old, u_new, u_old, var_
         else:
             new_vec, old_vec = u_new.vector(), u_old.vector()
         error[0] = df.norm(new_vec - old_vec + df.DOLFIN_EPS) / df.norm(old_vec + df.DOLFIN_EPS)
-        with open(error_file, "a") as log:
-            log.write(f"{error[0]:<23}  {dt_old.time_step:<23}  {dt.time_step:<23}\n")
-            log.flush()
+        if df.MPI.rank(df.MPI.comm_world) == 0:          # every rank holds the same (replicated) estimate: one row per attempt
+            with open(error_file, "a") as log:
+                log.write(f"{error[0]:<23}  {dt_old.time_step:<23}  {dt.time_step:<23}\n")
+                log.flush()
         max_error[0] = max(error)
         if error[0] >= ttol:
             raise ErrorGreaterThanTTOL

@@ -178,8 +178,9 @@ def test_user_script_runs_partitioned_under_torchrun(world):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-           "--master-port", str(29560 + world), str(ROOT / "tools" / "script_mgpu_check.py")]
-    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
-    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert "PASS" in r.stdout
+    for case in ("streamer", "glow"):
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+               "--master-port", str(29560 + world), str(ROOT / "tools" / "script_mgpu_check.py"), "--case", case]
+        r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+        assert "PASS" in r.stdout

@@ -21,12 +21,44 @@ import torch
 import torch.distributed as dist
 
 ap = argparse.ArgumentParser()
+ap.add_argument("--case", default="streamer", choices=["streamer", "glow"])
 ap.add_argument("--n", type=int, default=128)
 ap.add_argument("--steps", type=int, default=4)
 args = ap.parse_args()
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 
 import dolfin                                                     # the shim; creates the process group on first MPI use
+
+if args.case == "glow":
+    # the reference's glow-discharge test case (5 coupled equations, tables, adaptive BDF2, XDMF/HDF5 checkpoints) under N ranks:
+    # rank 0 writes the files; they must equal the FEniCS goldens like the 1-GPU run does (tests/test_gpu_shim.py)
+    import glow_discharge as gd
+    from fedm_b200.hdf5_lite import read_h5
+    gold = np.load(ROOT / "tests" / "golden" / "glow_h5.npz")
+    tmp = tempfile.mkdtemp() if rank == 0 else None
+    box = [tmp]
+    dist_ = dolfin.MPI._dist()
+    dist_.broadcast_object_list(box, src=0)
+    out = Path(box[0])
+    gd.main(input_dir=ROOT / "tests" / "golden" / "glow_discharge_input", output_dir=out)
+    dolfin.MPI.barrier()
+    ok = True
+    if rank == 0:
+        errs = {}
+        for name in ("electrons", "Ar_plus", "Ar_star"):
+            vecs = read_h5(out / "number density" / name / f"{name}.h5", name)
+            ref = gold[name + "_1"]
+            errs[name] = float(np.abs((vecs[1].ravel() - ref) / ref).max())
+        rows = (out / "relative error.log").read_text().splitlines()
+        ok = max(errs.values()) <= 1e-8 and len(rows) == 6
+        print(f"script_mgpu_check world={world} case=glow: rel errors vs FEniCS golden HDF5 {errs}, log rows {len(rows)} -> "
+              f"{'PASS' if ok else 'FAIL'}", flush=True)
+    flag = torch.tensor([1 if ok else 0], device=torch.device("cuda", local))
+    dist_.all_reduce(flag, op=dist_.ReduceOp.MIN)
+    dist_.barrier()
+    dist_.destroy_process_group()
+    sys.exit(0 if int(flag.item()) else 1)
+
 import streamer_discharge as sd
 
 with tempfile.TemporaryDirectory() as tmp:
