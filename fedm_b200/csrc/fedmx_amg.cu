@@ -13,6 +13,7 @@
 #include <string>
 
 #include <cooperative_groups.h>
+#include <cuda_fp16.h>
 
 #include "fedmx_internal.h"
 
@@ -27,7 +28,7 @@ enum { MODE_MULT = 0, MODE_RESID = 1, MODE_JACOBI = 2, MODE_ADD = 3, MODE_JACOBI
 
 // MODE_JACOBI_OUT: the last sweep of the cycle writes its result straight into component `yo` of the node-interleaved
 // preconditioned vector (y[row*ys + yo]) instead of the level's iterate.
-template <int MODE>
+template <int MODE, bool COMPACT = false>
 __global__ void __launch_bounds__(128) ssell_kernel(ScalarSell A, const double *__restrict__ x, const double *__restrict__ b,
                                                     const double *__restrict__ dinv, double omega, double *__restrict__ y,
                                                     int ys = 1, int yo = 0) {
@@ -37,25 +38,40 @@ __global__ void __launch_bounds__(128) ssell_kernel(ScalarSell A, const double *
     if (s >= A.n_slices) return;
     const int width = A.slice_width[s];
     const int64_t base = A.slice_ptr[s] + lane;
+    // entry k of this row: (value, column); COMPACT: FP16 value scaled by the row's diagonal, 16-bit column offset
+    auto entry = [&](int64_t e, double &v, int64_t &c) {
+        if (COMPACT) {
+            v = double(__half2float(__ushort_as_half(A.val16[e])));
+            c = row + A.col16[e];
+        } else {
+            v = double(A.val[e]);
+            c = A.col[e];
+        }
+    };
     double t = 0.0;
     if (MODE == MODE_FIRST_RESID) {
         // zero-guess sweep fused with the residual: x = omega Dinv b is formed on the fly at the neighbours (b and dinv are
         // gathered instead of x), x itself is written for the later prolongation:  y = b - A (omega Dinv b), ys/yo unused
         for (int k = 0; k < width; ++k) {
-            const int64_t e = base + int64_t(k) * FEDMX_SLICE;
-            const int32_t c = A.col[e];
-            t = fma(double(A.val[e]), omega * __ldg(dinv + c) * __ldg(b + c), t);
+            double v;
+            int64_t c;
+            entry(base + int64_t(k) * FEDMX_SLICE, v, c);
+            t = fma(v, omega * __ldg(dinv + c) * __ldg(b + c), t);
         }
         if (row >= A.n_rows) return;
+        if (COMPACT) t *= A.rdiag[row];
         const_cast<double *>(x)[row] = omega * dinv[row] * b[row];
         y[row] = b[row] - t;
         return;
     }
     for (int k = 0; k < width; ++k) {
-        const int64_t e = base + int64_t(k) * FEDMX_SLICE;
-        t = fma(double(A.val[e]), __ldg(x + A.col[e]), t);
+        double v;
+        int64_t c;
+        entry(base + int64_t(k) * FEDMX_SLICE, v, c);
+        t = fma(v, __ldg(x + c), t);
     }
     if (row >= A.n_rows) return;
+    if (COMPACT) t *= A.rdiag[row];
     if (MODE == MODE_MULT) y[row] = t;
     else if (MODE == MODE_RESID) y[row] = b[row] - t;
     else if (MODE == MODE_JACOBI) y[row] = x[row] + omega * dinv[row] * (b[row] - t);
@@ -145,6 +161,13 @@ __device__ __forceinline__ double ssell_row_part(const ScalarSell &M, int64_t ro
     const int width = M.slice_width[s];
     const int64_t base = M.slice_ptr[s] + lane;
     double t = 0.0;
+    if (M.val16) {                                               // compact finest operator (see ScalarSell)
+        for (int k = part; k < width; k += lpr) {
+            const int64_t e = base + int64_t(k) * FEDMX_SLICE;
+            t = fma(double(__half2float(__ushort_as_half(M.val16[e]))), x[row + M.col16[e]], t);
+        }
+        return t * M.rdiag[row];
+    }
     for (int k = part; k < width; k += lpr) {
         const int64_t e = base + int64_t(k) * FEDMX_SLICE;
         t = fma(double(M.val[e]), x[M.col[e]], t);
@@ -293,7 +316,7 @@ __global__ void comp_scatter_kernel(const double *__restrict__ e, double *__rest
 }
 
 int upload_ssell(fedmx_ctx *ctx, ScalarSell &M, int64_t n_rows, int64_t n_cols, const int32_t *rowptr, const int32_t *col,
-                 const double *val) {
+                 const double *val, bool try_compact = false) {
     M.n_rows = n_rows;
     M.n_cols = n_cols;
     M.n_slices = (n_rows + FEDMX_SLICE - 1) / FEDMX_SLICE;
@@ -306,6 +329,42 @@ int upload_ssell(fedmx_ctx *ctx, ScalarSell &M, int64_t n_rows, int64_t n_cols, 
         sw[s] = w;
         sp[s + 1] = sp[s] + int64_t(w) * FEDMX_SLICE;
     }
+    int rc;
+    int64_t *dsp; int32_t *dsw, *dc; float *dv;
+    if ((rc = fedmx_upload(ctx, &dsp, sp))) return rc;
+    if ((rc = fedmx_upload(ctx, &dsw, sw))) return rc;
+    M.val16 = nullptr; M.col16 = nullptr; M.rdiag = nullptr;
+    if (try_compact && n_rows == n_cols) {
+        // 4 bytes per nonzero: possible when every column offset fits 16 bits and every row has a non-zero diagonal
+        bool ok = true;
+        std::vector<double> diag(n_rows, 0.0);
+        for (int64_t r = 0; r < n_rows && ok; ++r)
+            for (int32_t q = rowptr[r]; q < rowptr[r + 1]; ++q) {
+                const int64_t d = int64_t(col[q]) - r;
+                if (d < -32768 || d > 32767) { ok = false; break; }
+                if (d == 0) diag[r] = val[q];
+            }
+        for (int64_t r = 0; r < n_rows && ok; ++r) ok = diag[r] != 0.0;
+        if (ok) {
+            std::vector<unsigned short> v16(sp[M.n_slices], 0);
+            std::vector<short> c16(sp[M.n_slices], 0);
+            for (int64_t r = 0; r < n_rows; ++r) {
+                const int64_t s = r / FEDMX_SLICE, l = r % FEDMX_SLICE;
+                for (int32_t q = rowptr[r]; q < rowptr[r + 1]; ++q) {
+                    const int64_t e = sp[s] + int64_t(q - rowptr[r]) * FEDMX_SLICE + l;
+                    c16[e] = short(int64_t(col[q]) - r);
+                    v16[e] = __half_as_ushort(__float2half_rn(float(val[q] / diag[r])));
+                }
+            }
+            unsigned short *dv16; short *dc16; double *dd;
+            if ((rc = fedmx_upload(ctx, &dv16, v16))) return rc;
+            if ((rc = fedmx_upload(ctx, &dc16, c16))) return rc;
+            if ((rc = fedmx_upload(ctx, &dd, diag))) return rc;
+            M.slice_ptr = dsp; M.slice_width = dsw; M.col = nullptr; M.val = nullptr;
+            M.val16 = dv16; M.col16 = dc16; M.rdiag = dd;
+            return FEDMX_OK;
+        }
+    }
     std::vector<int32_t> c(sp[M.n_slices], 0);
     std::vector<float> v(sp[M.n_slices], 0.0f);
     for (int64_t r = 0; r < n_rows; ++r) {
@@ -316,10 +375,6 @@ int upload_ssell(fedmx_ctx *ctx, ScalarSell &M, int64_t n_rows, int64_t n_cols, 
             v[e] = float(val[q]);
         }
     }
-    int rc;
-    int64_t *dsp; int32_t *dsw, *dc; float *dv;
-    if ((rc = fedmx_upload(ctx, &dsp, sp))) return rc;
-    if ((rc = fedmx_upload(ctx, &dsw, sw))) return rc;
     if ((rc = fedmx_upload(ctx, &dc, c))) return rc;
     if ((rc = fedmx_upload(ctx, &dv, v))) return rc;
     M.slice_ptr = dsp; M.slice_width = dsw; M.col = dc; M.val = dv;
@@ -331,7 +386,8 @@ void launch_ssell(fedmx_ctx *ctx, const ScalarSell &A, const double *x, const do
                   int ys = 1, int yo = 0) {
     const int threads = 128;
     const unsigned blocks = unsigned((A.n_slices * FEDMX_SLICE + threads - 1) / threads);
-    ssell_kernel<MODE><<<blocks, threads, 0, ctx->stream>>>(A, x, b, dinv, omega, y, ys, yo);
+    if (A.val16) ssell_kernel<MODE, true><<<blocks, threads, 0, ctx->stream>>>(A, x, b, dinv, omega, y, ys, yo);
+    else ssell_kernel<MODE><<<blocks, threads, 0, ctx->stream>>>(A, x, b, dinv, omega, y, ys, yo);
     ctx->launches++;
 }
 
@@ -631,7 +687,10 @@ extern "C" int fedmx_amg_add_level(fedmx_ctx *ctx, int64_t n, const double *h_di
     FEDMX_CHECK_CUDA(ctx, cudaMemset(lv.r, 0, nvec * sizeof(double)));
     if (n_coarse > 0) {
         FEDMX_REQUIRE(ctx, a_rowptr && p_rowptr && r_rowptr, "fedmx_amg_add_level: missing operators");
-        if ((rc = upload_ssell(ctx, lv.A, n, n, a_rowptr, a_col, a_val))) return rc;
+        // finest operator: compact 4-byte entries unless FEDMX_AMG_COMPACT=0 (it is the only multigrid array streamed from HBM)
+        static const bool env_compact = !(getenv("FEDMX_AMG_COMPACT") && atoi(getenv("FEDMX_AMG_COMPACT")) == 0);
+        const bool finest = ctx->amg_levels.empty();
+        if ((rc = upload_ssell(ctx, lv.A, n, finest ? nvec : n, a_rowptr, a_col, a_val, finest && env_compact && nvec == n))) return rc;
         if ((rc = upload_ssell(ctx, lv.P, n, n_coarse, p_rowptr, p_col, p_val))) return rc;
         if ((rc = upload_ssell(ctx, lv.R, n_coarse, n, r_rowptr, r_col, r_val))) return rc;
     }

@@ -95,6 +95,12 @@ struct ScalarSell {
     const float *val = nullptr;     // multigrid operators are stored in FP32 (vectors and arithmetic stay FP64): the
                                     // preconditioner is still one fixed linear operator, so GMRES is unaffected, and
                                     // the V-cycle moves 8 instead of 12 bytes per nonzero
+    // compact form of the finest operator (the only multigrid array that does not fit the L2): 4 bytes per nonzero.
+    // val16 = a_ij / a_ii in FP16 (row-scaled: |.| <= O(1), no range problem near the axis where 2 pi r -> 0),
+    // col16 = column - row, rdiag = a_ii in FP64.  Used when every offset fits 16 bits (one GPU; node-ordered meshes).
+    const unsigned short *val16 = nullptr;
+    const short *col16 = nullptr;
+    const double *rdiag = nullptr;
 };
 
 struct AmgLevel {

@@ -34,7 +34,11 @@ def test_two_stage_preconditioner_matches_numpy_cycle(n):
         l["dinv"] = d
     ref = amg.vcycle_reference(lv, coarse_inv, r[2::3], nu=1)
     err = np.abs(z[2::3] - ref).max() / np.abs(ref).max()
-    assert err < 2e-5, err                              # FP32 operator storage
+    # operator storage: FP32 on all levels; the finest operator additionally in the compact form (FP16 values scaled by the
+    # row diagonal, fedmx_amg.cu) unless FEDMX_AMG_COMPACT=0 -- a preconditioner only has to be a fixed linear operator
+    import os
+    compact = os.environ.get("FEDMX_AMG_COMPACT", "1") != "0"
+    assert err < (3e-3 if compact else 2e-5), err
     # stage 1: the transport components are the node-block Jacobi solve
     rowptr, col, vals = hot.matrix_bsr()
     diag = np.array([vals[rowptr[i] + list(col[rowptr[i]:rowptr[i + 1]]).index(i)] for i in range(0, hot.n_owned, max(1, hot.n_owned // 200))])
