@@ -93,13 +93,19 @@ __device__ __forceinline__ void fan_walk(const RowCtx &C, const RowPrefetch &pf,
     }
 #pragma unroll
     for (int k = 0; k < NEQ; ++k) R[k] = 0.0;
-    uint32_t pack = pf.pack0, cw = pf.cw0;
+    // fan entries are prefetched TWO cells ahead (one cell of arithmetic does not cover the global-load latency)
+    uint32_t pack = pf.pack0, cw = pf.cw0, pack1 = 0, cw1 = 0;
+    if (n_inc > 1) {
+        const int64_t e = ibase + FEDMX_SLICE + lane;
+        pack1 = C.inc_pack[e];
+        cw1 = C.inc_cell[e];
+    }
     for (int m = 0; m < n_inc; ++m) {
-        uint32_t pack1 = 0, cw1 = 0;
-        if (m + 1 < n_inc) {                                            // prefetch the next fan entry
-            const int64_t e = ibase + int64_t(m + 1) * FEDMX_SLICE + lane;
-            pack1 = C.inc_pack[e];
-            cw1 = C.inc_cell[e];
+        uint32_t pack2 = 0, cw2 = 0;
+        if (m + 2 < n_inc) {
+            const int64_t e = ibase + int64_t(m + 2) * FEDMX_SLICE + lane;
+            pack2 = C.inc_pack[e];
+            cw2 = C.inc_cell[e];
         }
         RowOut<NEQ> o;
         eval(cw, pack, o);
@@ -126,6 +132,8 @@ __device__ __forceinline__ void fan_walk(const RowCtx &C, const RowPrefetch &pf,
         }
         pack = pack1;
         cw = cw1;
+        pack1 = pack2;
+        cw1 = cw2;
     }
     if (bc) {
         const double g = C.bc_values[bc - 1];
