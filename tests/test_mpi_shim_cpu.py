@@ -24,7 +24,7 @@ WORKER = textwrap.dedent('''
     assert df.MPI.max(df.MPI.comm_world, mesh.hmax()) == mesh.hmax()
     text = utils.mesh_info(mesh) if hasattr(utils, "mesh_info") else ""
     df.MPI.barrier()
-    sys.stdout.write(f"rank{rank}ok\n")
+    sys.stdout.write("rank%dok\n" % rank)
 ''')
 
 
