@@ -3,34 +3,30 @@
 import os
 import subprocess
 import sys
-import textwrap
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
 
-WORKER = textwrap.dedent('''
-    import sys
-    sys.path.insert(0, {root!r})
-    from fedm_b200 import dolfin as df
-    from fedm_b200 import utils
-    rank, size = df.MPI.rank(df.MPI.comm_world), df.MPI.size(df.MPI.comm_world)
-    assert size == 2
-    assert df.MPI.sum(df.MPI.comm_world, rank + 1) == 3
-    assert df.MPI.max(df.MPI.comm_world, 10.0 * (rank + 1)) == 20.0
-    assert df.MPI.min(df.MPI.comm_world, 10.0 * (rank + 1)) == 10.0
-    mesh = df.RectangleMesh(df.Point(0.0, 0.0), df.Point(1.0, 2.0), 7, 9)
-    # every rank holds the whole mesh; the local cell counts are shares that add up to the global count
-    assert df.MPI.sum(df.MPI.comm_world, mesh.num_cells()) == 2 * 7 * 9
-    assert df.MPI.max(df.MPI.comm_world, mesh.hmax()) == mesh.hmax()
-    text = utils.mesh_info(mesh) if hasattr(utils, "mesh_info") else ""
-    df.MPI.barrier()
-    sys.stdout.write("rank%dok\n" % rank)
-''')
+WORKER = '''import sys
+sys.path.insert(0, ROOT_PATH)
+from fedm_b200 import dolfin as df
+rank, size = df.MPI.rank(df.MPI.comm_world), df.MPI.size(df.MPI.comm_world)
+assert size == 2
+assert df.MPI.sum(df.MPI.comm_world, rank + 1) == 3
+assert df.MPI.max(df.MPI.comm_world, 10.0 * (rank + 1)) == 20.0
+assert df.MPI.min(df.MPI.comm_world, 10.0 * (rank + 1)) == 10.0
+mesh = df.RectangleMesh(df.Point(0.0, 0.0), df.Point(1.0, 2.0), 7, 9)
+# every rank holds the whole mesh; the local cell counts are shares that add up to the global count
+assert df.MPI.sum(df.MPI.comm_world, mesh.num_cells()) == 2 * 7 * 9
+assert df.MPI.max(df.MPI.comm_world, mesh.hmax()) == mesh.hmax()
+df.MPI.barrier()
+sys.stdout.write("rank%dok " % rank)
+'''
 
 
 def test_mpi_shim_reductions_world_size_2(tmp_path):
     script = tmp_path / "worker.py"
-    script.write_text(WORKER.format(root=str(ROOT)))
+    script.write_text(WORKER.replace("ROOT_PATH", repr(str(ROOT))))
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", CUDA_VISIBLE_DEVICES="")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                         "--master-port", "29691", str(script)], env=env, capture_output=True, text=True, timeout=300)
