@@ -130,10 +130,12 @@ def algorithmic_bytes(nv, nc, n_eq=3, zero_entries=1):
     return asm, spmv, nnz
 
 
-def workload_config(n):
+def workload_config(n, ny=None):
     """The workload both arms run -- identical dict in the GPU line and in the `--impl reference` line."""
-    nv, nc = (n + 1) ** 2, 2 * n * n
-    return {"workload": f"synthetic streamer mesh n={n} (right grid), one accepted BDF2 step, Newton rtol 1e-4, GMRES(30) rtol 1e-5 "
+    ny = n if ny is None else ny
+    nv, nc = (n + 1) * (ny + 1), 2 * n * ny
+    shape = f"n={n}" if ny == n else f"{n}x{ny} cells"
+    return {"workload": f"synthetic streamer mesh {shape} (right grid), one accepted BDF2 step, Newton rtol 1e-4, GMRES(30) rtol 1e-5 "
                         "(reference test semantics)",
             "dof": 3 * nv, "cells": nc, "nnz": 9 * (nv + 2 * (nv + nc - 1)), "l2": "inputs larger than L2 (no flush)"}
 
@@ -171,6 +173,8 @@ def main():
     ap.add_argument("--precond", default="amg", choices=["amg", "ilu0", "bjacobi"],
                     help="amg (default): two-stage AMG + node-block Jacobi; ilu0: the reference test's literal PC (PETSc default for "
                          "linear_solver='gmres': ILU(0), block Jacobi across GPUs) -- reports its Krylov iterations per step")
+    ap.add_argument("--weak", action="store_true", help="weak scaling: n*sqrt(N) x n*sqrt(N) cells of the same domain (isotropic "
+                                                          "refinement), i.e. ~10 M DOF PER GPU; the default is strong scaling of the fixed n x n mesh")
     ap.add_argument("--profile-detail", action="store_true", help="nested event timing of multigrid levels and collectives")
     args = ap.parse_args()
 
@@ -194,7 +198,11 @@ def main():
     from fedm_b200.streamer import StreamerCase
 
     t_setup = time.time()
-    case = StreamerCase(n=args.n, device=local_rank, world=world, rank=rank, precond=args.precond)
+    n_base = args.n
+    if args.weak:                                  # same DOF per GPU: refine both directions by sqrt(N) (cells stay isotropic)
+        args.n = int(round(args.n * world ** 0.5))
+    ny = args.n
+    case = StreamerCase(n=args.n, ny=ny, device=local_rank, world=world, rank=rank, precond=args.precond)
     case.set_initial_state(bench_initial_potential=True)
     setup_s = time.time() - t_setup
     hot = case.hot
@@ -267,7 +275,7 @@ def main():
     parity = None
     if not args.no_parity:
         kw = dict(ksp_rtol=1e-13, ksp_max_it=50000) if world == 1 else {}
-        ref_case = StreamerCase(n=args.n, device=local_rank, **kw)           # always the default preconditioner
+        ref_case = StreamerCase(n=args.n, ny=ny, device=local_rank, **kw)    # always the default preconditioner
         ref_case.set_initial_state(bench_initial_potential=True)
         for _ in range(steps_taken):                                   # (run() would stop at its default T_final)
             ref_case.step()
@@ -304,9 +312,9 @@ def main():
     line = {
         "metric": "streamer BDF2 steps/s (synthetic 10.0M-DOF mesh)",
         "value": args.steps / (ms * 1e-3), "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak" if args.weak else "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args.n),
+        "config": workload_config(args.n, ny),
         "solver": {"linear": "GMRES(30), classical Gram-Schmidt with one reduction per iteration, left PC, rtol 1e-5",
                    "preconditioner": {"amg": "two-stage: AMG V(1,1) on the potential block + node-block Jacobi",
                                       "ilu0": "ILU(0) per GPU block (multicolour ordering), block Jacobi across GPUs: the reference test's PC",
@@ -314,6 +322,8 @@ def main():
                    "matrix_format": "SELL-32 3x3 node blocks, FP64; the structurally zero block entry (1 of 9) is kept in the "
                                     "exported dolfin pattern but not streamed",
                    "parallelism": f"vertex partition x{world}" if world > 1 else "single GPU"},
+        "gdof_steps_per_s": dof * args.steps / (ms * 1e-3) / 1e9,        # throughput in unknowns advanced per second (weak-scaling figure)
+        "weak_scaling": {"n_per_gpu_base": n_base, "n": args.n, "dof_per_gpu": dof / world} if args.weak else None,
         "attempts": attempts, "newton_its_per_step": newton_its / args.steps, "krylov_its_per_step": krylov_its / args.steps,
         "jacobian_assembly_gdof_s": (dof * n_aj / (ms_aj * 1e-3) / 1e9) if ms_aj > 0 else None,
         "residual_assembly_gdof_s": (dof * n_ar / (ms_ar * 1e-3) / 1e9) if ms_ar > 0 else None,

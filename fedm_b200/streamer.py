@@ -24,18 +24,20 @@ STREAMER_PARAMS = [2.3987, -0.26, 4.3628e-3, 0.22, 1.1944e6, 4.3666e26, 2.73e7, 
                    ELEMENTARY_CHARGE / EPSILON_0, float((1 << 1) | (1 << 2))]
 
 
-def streamer_mesh(n, grading_power=1.0):
+def streamer_mesh(n, grading_power=1.0, ny=None):
+    """n x ny (default n x n) 'right' grid of the 1.25 cm x 1.25 cm gap; ny != n gives the weak-scaling meshes of bench.py."""
+    ny = n if ny is None else ny
     if grading_power == 1.0:
-        return rectangle((0.0, 0.0), (BOX, BOX), n, n, "right")
-    return rectangle((0.0, 0.0), (BOX, BOX), n, n, "right", map_x=lambda s: s ** grading_power)
+        return rectangle((0.0, 0.0), (BOX, BOX), n, ny, "right")
+    return rectangle((0.0, 0.0), (BOX, BOX), n, ny, "right", map_x=lambda s: s ** grading_power)
 
 
 class StreamerCase:
     n_eq = 3
 
     def __init__(self, n=64, grading_power=1.0, device=0, mesh=None, newton_rtol=1e-4, newton_max_it=20,
-                 ksp_rtol=1e-5, ksp_restart=30, ksp_max_it=10000, world=1, rank=0, precond="amg"):
-        gmesh = mesh if mesh is not None else streamer_mesh(n, grading_power)
+                 ksp_rtol=1e-5, ksp_restart=30, ksp_max_it=10000, world=1, rank=0, precond="amg", ny=None):
+        gmesh = mesh if mesh is not None else streamer_mesh(n, grading_power, ny)
         self.global_vertices, self.global_cells = gmesh.num_vertices, gmesh.num_cells
         self.world, self.rank = world, rank
         fv = gmesh.exterior_facets()
