@@ -97,6 +97,21 @@ class HotPath:
         self._ck(self.lib.fedmx_pattern_get(self.h, C.byref(nr), C.byref(nz), _np_ptr(rowptr), _np_ptr(colidx)))
         return rowptr, colidx
 
+    def dofmap_fenics(self):
+        """dof -> vertex map of dolfin's serial P1 numbering for this context's mesh (fedmx_dofmap_fenics)."""
+        d2v = np.empty(self.n_vertices, dtype=np.int32)
+        self._ck(self.lib.fedmx_dofmap_fenics(self.h, _np_ptr(d2v)))
+        return d2v
+
+    def pattern_fenics(self):
+        """dolfin's scalar SparsityPattern in dolfin's own dof numbering (rows/columns n_eq*dof + comp): (indptr, indices)."""
+        nr, nz = C.c_int64(), C.c_int64()
+        self._ck(self.lib.fedmx_pattern_get_fenics(self.h, C.byref(nr), C.byref(nz), None, None))
+        indptr = np.empty(nr.value + 1, dtype=np.int64)
+        indices = np.empty(nz.value, dtype=np.int32)
+        self._ck(self.lib.fedmx_pattern_get_fenics(self.h, C.byref(nr), C.byref(nz), _np_ptr(indptr), _np_ptr(indices)))
+        return indptr, indices
+
     def matrix_bsr(self):
         rowptr, colidx = self.pattern()
         vals = np.empty((colidx.size, self.n_eq, self.n_eq))
