@@ -556,29 +556,38 @@ int fedmx_amg_vcycle(fedmx_ctx *ctx, double *z_out, int z_stride, int z_off) {
         return FEDMX_OK;
     };
     if (cf >= 1 && (rc = down_level(0))) return rc;
-    const bool use_graph = env_graph && cf >= 2 && nu == 1 && ctx->prof_on < 2 && ctx->coarse_grid_blocks == 0 && ctx->stream != 0;
+    const bool use_graph = env_graph && cf >= 2 && nu == 1 && ctx->prof_on < 2 && ctx->coarse_grid_blocks == 0 && ctx->stream != 0 && !ctx->mg_graph_off;
     if (cf == 0) {
         if ((rc = coarse_levels())) return rc;
     } else if (!use_graph) {
         if ((rc = replicated_section())) return rc;
     } else {
         cudaGraphExec_t &exec = ctx->mg_graph[ctx->mg_parity];
+        bool launched = false;
         if (!exec) {
+            // capture this cycle's section; if the driver refuses (capture unsupported in this context), run it directly and
+            // stop trying
             const int64_t before = ctx->launches;
             cudaGraph_t graph = nullptr;
-            FEDMX_CHECK_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-            rc = replicated_section();                     // recorded, not executed; performs this cycle's x/x2 swaps
-            cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
-            if (rc) return rc;
-            FEDMX_CHECK_CUDA(ctx, ce);
-            FEDMX_CHECK_CUDA(ctx, cudaGraphInstantiate(&exec, graph, 0));
-            cudaGraphDestroy(graph);
-            ctx->mg_graph_nodes = int(ctx->launches - before);
+            if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+                cudaGetLastError();
+                ctx->mg_graph_off = true;
+                if ((rc = replicated_section())) return rc;
+                launched = true;
+            } else {
+                rc = replicated_section();                 // recorded, not executed; performs this cycle's x/x2 swaps
+                cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+                if (rc) return rc;
+                if (ce == cudaSuccess) ce = cudaGraphInstantiate(&exec, graph, 0);
+                if (graph) cudaGraphDestroy(graph);
+                FEDMX_CHECK_CUDA(ctx, ce);
+                ctx->mg_graph_nodes = int(ctx->launches - before);
+            }
         } else {
             for (int l = 1; l < cf; ++l) std::swap(L[l].x, L[l].x2);      // what the section does on the host
             ctx->launches += ctx->mg_graph_nodes;
         }
-        FEDMX_CHECK_CUDA(ctx, cudaGraphLaunch(exec, ctx->stream));
+        if (!launched) FEDMX_CHECK_CUDA(ctx, cudaGraphLaunch(exec, ctx->stream));
         ctx->mg_parity ^= 1;
     }
     if (cf >= 1 && (rc = up_level(0))) return rc;

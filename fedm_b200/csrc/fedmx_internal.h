@@ -184,6 +184,7 @@ struct fedmx_ctx {
     int precond_kind = 0, amg_comp = 0, amg_nu = 1;
     cudaGraphExec_t mg_graph[2] = {nullptr, nullptr};   // replicated multigrid levels, one graph per x/x2 ping-pong parity
     int mg_parity = 0, mg_graph_nodes = 0;
+    bool mg_graph_off = false;       // stream capture was refused once: plain launches from then on
     bool amg_v01 = false;            // finest multigrid level runs a V(0,1) cycle (see fedmx_amg_vcycle)
     std::vector<AmgLevel> amg_levels;
     double *amg_coarse_inv = nullptr;
