@@ -2,10 +2,12 @@
 // kernels the form compiler generates.
 #pragma once
 
+// N = 0 is the value-only instantiation (residual-only kernels run the same generated expression code without paying for
+// derivative lanes); its one-element array is never touched.
 template <int N>
 struct Dual {
     double v;
-    double d[N];
+    double d[N > 0 ? N : 1];
 };
 
 template <int N> __device__ __forceinline__ Dual<N> dconst(double c) {
@@ -88,7 +90,7 @@ template <int N> __device__ __forceinline__ Dual<N> dlog(const Dual<N> &a) {
 }
 // a^c for a constant real exponent
 template <int N> __device__ __forceinline__ Dual<N> dpow(const Dual<N> &a, double c) {
-    Dual<N> r; r.v = pow(a.v, c); const double f = c * pow(a.v, c - 1.0);
+    Dual<N> r; r.v = pow(a.v, c); const double f = c * r.v / a.v;          // one pow(): d/da a^c = c a^c / a
 #pragma unroll
     for (int i = 0; i < N; ++i) r.d[i] = f * a.d[i];
     return r;

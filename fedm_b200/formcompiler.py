@@ -354,9 +354,10 @@ class CompiledForm:
         L.append("    static constexpr int MINB = 2, MINB_RES = 2;")
         L.append("    static constexpr unsigned ZERO_MASK = 0;")
         L.append(f"    static constexpr int NEQ = {neq};\n    static constexpr int NF = {nf};\n    static constexpr int NC = 0;")
-        L.append(f"    typedef Dual<{nd}> D;\n    typedef Vtx<{neq}, {nf}, 0> V;")
+        L.append(f"    typedef Vtx<{neq}, {nf}, 0> V;")
         L.append("    template <bool JAC>")
         L.append(f"    static __device__ __noinline__ void row(const ModelParams &mp, const V &a, const V &p, const V &n, uint32_t mk_ap, uint32_t mk_an, RowOut<{neq}> &o) {{")
+        L.append(f"        typedef Dual<JAC ? {nd} : 0> D;          // residual-only: the same expression code on value-only duals")
         L.append("        const double e1r = p.r - a.r, e1z = p.z - a.z, e2r = n.r - a.r, e2z = n.z - a.z;")
         L.append("        const double det = e1r * e2z - e1z * e2r, inv = 1.0 / det, adet = fabs(det);")
         L.append("        const double g_r[3] = {-(e2z - e1z) * inv, e2z * inv, -e1z * inv};")
@@ -367,8 +368,8 @@ class CompiledForm:
         for k in sorted(self.used_gu):
             for i, g in enumerate(("g_r", "g_z")):
                 L.append(f"        D gu{k}_{i}; gu{k}_{i}.v = a.u[{k}] * {g}[0] + p.u[{k}] * {g}[1] + n.u[{k}] * {g}[2];")
-                L.append(f"        for (int i = 0; i < {nd}; ++i) gu{k}_{i}.d[i] = 0.0;")
-                L.append(f"        gu{k}_{i}.d[{k}] = {g}[0]; gu{k}_{i}.d[{neq + k}] = {g}[1]; gu{k}_{i}.d[{2 * neq + k}] = {g}[2];")
+                L.append(f"        if constexpr (JAC) {{ for (int i = 0; i < {nd}; ++i) gu{k}_{i}.d[i] = 0.0; "
+                         f"gu{k}_{i}.d[{k}] = {g}[0]; gu{k}_{i}.d[{neq + k}] = {g}[1]; gu{k}_{i}.d[{2 * neq + k}] = {g}[2]; }}")
         for j in sorted(self.used_gf):
             for i, g in enumerate(("g_r", "g_z")):
                 L.append(f"        const double gf{j}_{i} = a.f[{j}] * {g}[0] + p.f[{j}] * {g}[1] + n.f[{j}] * {g}[2];")
@@ -380,14 +381,15 @@ class CompiledForm:
                 L.append(f"        nv{k}[{b}] = interp_fn{k}({w[0]!r} * a.r + {w[1]!r} * p.r + {w[2]!r} * n.r, {w[0]!r} * a.z + {w[1]!r} * p.z + {w[2]!r} * n.z, mp);")
         L += ["        " + ln for ln in em.cell_lines]
         L.append(f"        D R[{neq}];")
-        L.append(f"        for (int k = 0; k < {neq}; ++k) {{ R[k].v = 0.0; for (int i = 0; i < {nd}; ++i) R[k].d[i] = 0.0; }}")
+        L.append(f"        for (int k = 0; k < {neq}; ++k) {{ R[k].v = 0.0; if constexpr (JAC) for (int i = 0; i < {nd}; ++i) R[k].d[i] = 0.0; }}")
 
         def point_prelude(l0, l1, l2, indent):
             P = []
             P.append(f"const double xq0 = {l0} * a.r + {l1} * p.r + {l2} * n.r, xq1 = {l0} * a.z + {l1} * p.z + {l2} * n.z;")
             for k in sorted(self.used_u):
-                P.append(f"D u{k}; u{k}.v = {l0} * a.u[{k}] + {l1} * p.u[{k}] + {l2} * n.u[{k}]; for (int i = 0; i < {nd}; ++i) u{k}.d[i] = 0.0; "
-                         f"u{k}.d[{k}] = {l0}; u{k}.d[{neq + k}] = {l1}; u{k}.d[{2 * neq + k}] = {l2};")
+                P.append(f"D u{k}; u{k}.v = {l0} * a.u[{k}] + {l1} * p.u[{k}] + {l2} * n.u[{k}]; "
+                         f"if constexpr (JAC) {{ for (int i = 0; i < {nd}; ++i) u{k}.d[i] = 0.0; "
+                         f"u{k}.d[{k}] = {l0}; u{k}.d[{neq + k}] = {l1}; u{k}.d[{2 * neq + k}] = {l2}; }}")
             for j in sorted(self.used_fval):
                 P.append(f"const double fv{j} = {l0} * a.f[{j}] + {l1} * p.f[{j}] + {l2} * n.f[{j}];")
             for k, ip in enumerate(self.interps):
@@ -423,7 +425,7 @@ class CompiledForm:
             L.append("        }")
         L.append(f"        for (int k = 0; k < {neq}; ++k) {{")
         L.append("            o.R[k] = R[k].v;")
-        L.append(f"            if (JAC) for (int bb = 0; bb < 3; ++bb) for (int l = 0; l < {neq}; ++l) o.J[bb][k * {neq} + l] = R[k].d[bb * {neq} + l];")
+        L.append(f"            if constexpr (JAC) for (int bb = 0; bb < 3; ++bb) for (int l = 0; l < {neq}; ++l) o.J[bb][k * {neq} + l] = R[k].d[bb * {neq} + l];")
         L.append("        }")
         L.append("    }")
         L.append("};")
