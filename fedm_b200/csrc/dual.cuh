@@ -96,4 +96,7 @@ template <int N> __device__ __forceinline__ Dual<N> dpow(const Dual<N> &a, doubl
     return r;
 }
 template <int N> __device__ __forceinline__ double dsign(const Dual<N> &a) { return (a.v > 0.0) ? 1.0 : ((a.v < 0.0) ? -1.0 : 0.0); }
+#ifndef FEDMX_DSIGN_DOUBLE
+#define FEDMX_DSIGN_DOUBLE
 __device__ __forceinline__ double dsign(double a) { return (a > 0.0) ? 1.0 : ((a < 0.0) ? -1.0 : 0.0); }
+#endif

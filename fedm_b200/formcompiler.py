@@ -4,7 +4,8 @@ This is the B200 counterpart of the reference's FFC/uflacs + dijitso tool chain 
 ``J = derivative(F, u_new, u)``, fedm_streamer.py:296-297): the weak form a script builds through the fedm.functions API
 is lowered to a ``struct JitModel`` for the generic row kernel (``fedm_b200/csrc/row_kernel.cuh``).  Per quadrature
 point the integrand is written as  sum_k s_k v_k + f_k . grad(v_k)  (``ufl.test_function_split``); s_k and f_k are emitted
-as straight-line code over ``Dual<3*n_eq>`` numbers, so the Jacobian row comes out of forward-mode AD in registers.
+as straight-line code over component-sparse dual numbers (``csrc/cdual.cuh``: a sub-expression carries derivative
+lanes only for the unknown components it depends on), so the Jacobian row comes out of forward-mode AD in registers.
 Cell-constant sub-expressions (everything built from gradients of P1 fields, e.g. mu(|grad Phi|)) are hoisted out of the
 quadrature loop.  Quadrature follows FFC: the global ``quadrature_degree`` if set, else UFL's estimated degree of the
 summed integrand; FIAT's default triangle schemes, Gauss-Legendre on facets; non-symmetric rules are oriented by
@@ -114,7 +115,7 @@ class _Emitter:
     def _new(self, code, dual, cell):
         self.n += 1
         name = f"t{self.n}"
-        line = f"const {'D' if dual else 'double'} {name} = {code};"
+        line = f"const {'auto' if dual else 'double'} {name} = {code};"
         (self.cell_lines if cell else self.scope_lines).append(line)
         return name
 
@@ -242,7 +243,7 @@ class CompiledForm:
         self.source = self._generate()
         # the cache key covers the library headers the plug-in is compiled against (AsmArgs / ModelParams layout)
         h = hashlib.sha1(self.source.encode())
-        for name in ("row_kernel.cuh", "fedmx_internal.h", "dual.cuh"):
+        for name in ("row_kernel.cuh", "fedmx_internal.h", "cdual.cuh"):
             h.update((HERE / "csrc" / name).read_bytes())
         h.update((HERE.parent / "include" / "fedmx.h").read_bytes())
         self.key = h.hexdigest()[:20]
@@ -308,7 +309,7 @@ class CompiledForm:
 
     # ---- code generation
     def _generate(self):
-        neq, nd = self.n_eq, 3 * self.n_eq
+        neq = self.n_eq
         em = _Emitter(self)
         cell_blocks, facet_blocks, tables = [], [], []
 
@@ -345,7 +346,7 @@ class CompiledForm:
         L = []
         L.append("// Generated by fedm_b200/formcompiler.py -- do not edit.")
         L.append('#include "row_kernel.cuh"')
-        L.append('#include "dual.cuh"')
+        L.append('#include "cdual.cuh"')
         L.append("namespace {")
         L += tables
         for k, ip in enumerate(self.interps):
@@ -357,7 +358,9 @@ class CompiledForm:
         L.append(f"    typedef Vtx<{neq}, {nf}, 0> V;")
         L.append("    template <bool JAC>")
         L.append(f"    static __device__ __noinline__ void row(const ModelParams &mp, const V &a, const V &p, const V &n, uint32_t mk_ap, uint32_t mk_an, RowOut<{neq}> &o) {{")
-        L.append(f"        typedef Dual<JAC ? {nd} : 0> D;          // residual-only: the same expression code on value-only duals")
+        if neq > 16:
+            raise NotImplementedError("more than 16 unknown components")
+        L.append(f"        constexpr unsigned ALL = JAC ? {(1 << neq) - 1}u : 0u;   // residual-only: the same code on value-only duals")
         L.append("        const double e1r = p.r - a.r, e1z = p.z - a.z, e2r = n.r - a.r, e2z = n.z - a.z;")
         L.append("        const double det = e1r * e2z - e1z * e2r, inv = 1.0 / det, adet = fabs(det);")
         L.append("        const double g_r[3] = {-(e2z - e1z) * inv, e2z * inv, -e1z * inv};")
@@ -367,9 +370,8 @@ class CompiledForm:
         L.append("        const int ra = (a.id > p.id) + (a.id > n.id), rp = (p.id > a.id) + (p.id > n.id), rn = 3 - ra - rp;")
         for k in sorted(self.used_gu):
             for i, g in enumerate(("g_r", "g_z")):
-                L.append(f"        D gu{k}_{i}; gu{k}_{i}.v = a.u[{k}] * {g}[0] + p.u[{k}] * {g}[1] + n.u[{k}] * {g}[2];")
-                L.append(f"        if constexpr (JAC) {{ for (int i = 0; i < {nd}; ++i) gu{k}_{i}.d[i] = 0.0; "
-                         f"gu{k}_{i}.d[{k}] = {g}[0]; gu{k}_{i}.d[{neq + k}] = {g}[1]; gu{k}_{i}.d[{2 * neq + k}] = {g}[2]; }}")
+                L.append(f"        const auto gu{k}_{i} = cd_seed<JAC ? {1 << k}u : 0u>(a.u[{k}] * {g}[0] + p.u[{k}] * {g}[1] + "
+                         f"n.u[{k}] * {g}[2], {g}[0], {g}[1], {g}[2]);")
         for j in sorted(self.used_gf):
             for i, g in enumerate(("g_r", "g_z")):
                 L.append(f"        const double gf{j}_{i} = a.f[{j}] * {g}[0] + p.f[{j}] * {g}[1] + n.f[{j}] * {g}[2];")
@@ -380,16 +382,15 @@ class CompiledForm:
             for b, w in enumerate(nodes):
                 L.append(f"        nv{k}[{b}] = interp_fn{k}({w[0]!r} * a.r + {w[1]!r} * p.r + {w[2]!r} * n.r, {w[0]!r} * a.z + {w[1]!r} * p.z + {w[2]!r} * n.z, mp);")
         L += ["        " + ln for ln in em.cell_lines]
-        L.append(f"        D R[{neq}];")
-        L.append(f"        for (int k = 0; k < {neq}; ++k) {{ R[k].v = 0.0; if constexpr (JAC) for (int i = 0; i < {nd}; ++i) R[k].d[i] = 0.0; }}")
+        L.append(f"        CD<ALL> R[{neq}];")
+        L.append(f"        for (int k = 0; k < {neq}; ++k) R[k] = cd_zero<ALL>();")
 
         def point_prelude(l0, l1, l2, indent):
             P = []
             P.append(f"const double xq0 = {l0} * a.r + {l1} * p.r + {l2} * n.r, xq1 = {l0} * a.z + {l1} * p.z + {l2} * n.z;")
             for k in sorted(self.used_u):
-                P.append(f"D u{k}; u{k}.v = {l0} * a.u[{k}] + {l1} * p.u[{k}] + {l2} * n.u[{k}]; "
-                         f"if constexpr (JAC) {{ for (int i = 0; i < {nd}; ++i) u{k}.d[i] = 0.0; "
-                         f"u{k}.d[{k}] = {l0}; u{k}.d[{neq + k}] = {l1}; u{k}.d[{2 * neq + k}] = {l2}; }}")
+                P.append(f"const auto u{k} = cd_seed<JAC ? {1 << k}u : 0u>({l0} * a.u[{k}] + {l1} * p.u[{k}] + {l2} * n.u[{k}], "
+                         f"{l0}, {l1}, {l2});")
             for j in sorted(self.used_fval):
                 P.append(f"const double fv{j} = {l0} * a.f[{j}] + {l1} * p.f[{j}] + {l2} * n.f[{j}];")
             for k, ip in enumerate(self.interps):
@@ -425,7 +426,7 @@ class CompiledForm:
             L.append("        }")
         L.append(f"        for (int k = 0; k < {neq}; ++k) {{")
         L.append("            o.R[k] = R[k].v;")
-        L.append(f"            if constexpr (JAC) for (int bb = 0; bb < 3; ++bb) for (int l = 0; l < {neq}; ++l) o.J[bb][k * {neq} + l] = R[k].d[bb * {neq} + l];")
+        L.append(f"            if constexpr (JAC) for (int bb = 0; bb < 3; ++bb) for (int l = 0; l < {neq}; ++l) o.J[bb][k * {neq} + l] = R[k].d[3 * l + bb];")
         L.append("        }")
         L.append("    }")
         L.append("};")

@@ -107,6 +107,47 @@ def test_form_compiler_generates_and_cross_compiles_a_plugin(tmp_path, monkeypat
     assert cf.build() == so                                                       # second call hits the cache
 
 
+def _host_run(tmp_path, source, *defs):
+    """g++-compile a host test program against the library's dual-number headers (CUDA qualifiers defined away)."""
+    import shutil
+    import subprocess
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    gxx = "/usr/bin/g++" if Path("/usr/bin/g++").exists() else shutil.which("g++")
+    if gxx is None:
+        pytest.skip("no g++")
+    exe = tmp_path / "host_test"
+    cmd = [gxx, "-std=c++17", "-O1", "-I", str(root / "tools" / "jitcheck" / "stub"), "-I", str(root / "fedm_b200" / "csrc"),
+           *defs, "-o", str(exe), str(root / "tests" / "csrc" / source)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-3000:]
+    return r.stdout
+
+
+def test_component_sparse_duals_match_finite_differences_and_dense_duals(tmp_path):
+    """csrc/cdual.cuh (what generated kernels compute with): every operator against central differences, bit-equal with the
+    dense Dual<9> on the live lanes, and lane counts follow the component masks."""
+    assert "bad 0" in _host_run(tmp_path, "cdual_fd.cpp")
+
+
+def test_generated_rows_have_the_exact_jacobian_of_their_residual(tmp_path):
+    """J = derivative(F, u) (fedm_streamer.py:296-297): the generated row<true> of the time-of-flight form and of every cached
+    multi-component form (streamer n_eq = 3, glow n_eq = 5) against central differences of row<false>, compiled for the host."""
+    from fedm_b200 import formcompiler as fc
+    df.parameters["form_compiler"]["quadrature_degree"] = None
+    form, u_new = _tof_form(df.RectangleMesh(df.Point(0, 0), df.Point(1, 1), 2, 2))
+    cf = fc.CompiledForm(form, u_new, 4)
+    src = tmp_path / "tof_form.cu"
+    src.write_text(cf.source)
+    sources = [src] + [f for f in sorted(fc.CACHE.glob("form_*.cu")) if "NEQ = 1;" not in f.read_text()
+                       and '#include "cdual.cuh"' in f.read_text()]
+    for f in sources:
+        out = _host_run(tmp_path, "jit_row_fd.cpp", f'-DFORM="{f}"')
+        assert "bad 0" in out, (f.name, out[-2000:])
+
+
 def _write_dolfin_xml(path, coords, cells):
     lines = ['<?xml version="1.0"?>', '<dolfin xmlns:dolfin="http://fenicsproject.org">', '  <mesh celltype="triangle" dim="2">',
              f'    <vertices size="{len(coords)}">']

@@ -1,0 +1,22 @@
+#include FORM
+#include "harness.inc"
+__global__ void run(const Case *cs, ModelParams mp, double *out, int n) {
+    constexpr int NEQ = JitModel::NEQ;
+    int t = blockIdx.x * blockDim.x + threadIdx.x; if (t >= n) return;
+    RowOut<NEQ> o, o0;
+    JitModel::row<true>(mp, cs[t].v[0], cs[t].v[1], cs[t].v[2], cs[t].m1, cs[t].m2, o);
+    JitModel::row<false>(mp, cs[t].v[0], cs[t].v[1], cs[t].v[2], cs[t].m1, cs[t].m2, o0);
+    double *w = out + size_t(t) * kPer;
+    for (int k = 0; k < NEQ; ++k) { w[k] = o.R[k]; w[NEQ + k] = o0.R[k]; }
+    for (int b = 0; b < 3; ++b) for (int e = 0; e < NEQ * NEQ; ++e) w[2 * NEQ + b * NEQ * NEQ + e] = o.J[b][e];
+}
+int main(int argc, char **argv) {
+    std::vector<Case> cs; ModelParams mp; memset(&mp, 0, sizeof(mp)); make_cases(cs, mp, 256);
+    Case *d; double *o; cudaMalloc(&d, cs.size() * sizeof(Case)); cudaMalloc(&o, cs.size() * kPer * 8);
+    cudaMemcpy(d, cs.data(), cs.size() * sizeof(Case), cudaMemcpyHostToDevice);
+    run<<<4, 64>>>(d, mp, o, 256);
+    std::vector<double> h(cs.size() * kPer);
+    cudaError_t e = cudaMemcpy(h.data(), o, h.size() * 8, cudaMemcpyDeviceToHost);
+    printf("cuda: %s\n", cudaGetErrorString(e));
+    FILE *f = fopen(argv[1], "wb"); fwrite(h.data(), 8, h.size(), f); fclose(f);
+}
