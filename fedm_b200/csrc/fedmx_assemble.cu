@@ -13,6 +13,8 @@
 // Storage is SELL-32 with entry-major groups (fedmx_internal.h): the 32 lanes of a warp own 32 consecutive
 // rows, so every store instruction writes 256 contiguous bytes.
 // Dirichlet rows are fused into the epilogue: b_i = x_i - g, Jacobian row = unit row (pattern kept).
+#include <algorithm>
+
 #include "quadrature_tables.h"
 
 #include "row_kernel.cuh"
@@ -600,7 +602,7 @@ __global__ void nodal_exp6_kernel(const double *__restrict__ x, int n_eq, int nc
 
 template <class Model>
 int launch_assembly(fedmx_ctx *ctx, const double *d_x, double *d_b, bool jac) {
-    AsmArgs A;
+    AsmArgs A{};
     // cell-batch (tiled) kernel for the models that provide cell records; FEDMX_ASM_TILED=0 forces the generic row kernel
     static const bool env_tiled = !(getenv("FEDMX_ASM_TILED") && atoi(getenv("FEDMX_ASM_TILED")) == 0);
     if constexpr (Model::TILED) {
@@ -679,7 +681,7 @@ int assemble_dispatch(fedmx_ctx *ctx, const double *d_x, double dt, double dt_ol
             return launch_assembly<ProjectionModel>(ctx, d_x, d_b, jac);
         case FEDMX_MODEL_PLUGIN: {
             FEDMX_REQUIRE(ctx, ctx->plugin_launch, "assemble: no plug-in loaded");
-            AsmArgs A;
+            AsmArgs A{};
             A.S = ctx->sell;
             A.coords = ctx->d_coords;
             A.x = d_x;
@@ -689,9 +691,44 @@ int assemble_dispatch(fedmx_ctx *ctx, const double *d_x, double dt, double dt_ol
             A.val = jac ? ctx->d_val : nullptr;
             A.res = d_b;
             A.mp = ctx->mp;
+            // Cell-wise path (row_kernel.cuh): the plug-in evaluates every cell ONCE into a scratch record and the rows
+            // gather; needs cells * doubles-per-cell of scratch (5.1 GB for n_eq = 3 at 6.7 M cells), allocated on first
+            // use.  FEDMX_JIT_CELLS=0 or a refused allocation (cap FEDMX_CELL_SCRATCH_MAX_GB, default 32) = row-wise path.
+            static const bool env_cells = !(getenv("FEDMX_JIT_CELLS") && atoi(getenv("FEDMX_JIT_CELLS")) == 0);
+            if (env_cells && ctx->plugin_cell_doubles && ctx->n_cells > 0 && !ctx->cell_scratch_refused) {
+                const size_t need = size_t((ctx->n_cells + FEDMX_SLICE - 1) / FEDMX_SLICE * FEDMX_SLICE) * size_t(std::max(ctx->plugin_cell_doubles(1), ctx->plugin_cell_doubles(0)));
+                if (need > 0 && need > ctx->cell_scratch_doubles) {
+                    static const double cap_gb = getenv("FEDMX_CELL_SCRATCH_MAX_GB") ? atof(getenv("FEDMX_CELL_SCRATCH_MAX_GB")) : 32.0;
+                    size_t free_b = 0, total_b = 0;
+                    cudaMemGetInfo(&free_b, &total_b);
+                    void *buf = nullptr;
+                    if (ctx->d_cell_scratch) {                      // another plug-in with larger records was loaded
+                        auto &od = ctx->owned_device;
+                        od.erase(std::remove(od.begin(), od.end(), (void *)ctx->d_cell_scratch), od.end());
+                        cudaStreamSynchronize(ctx->stream);
+                        cudaFree(ctx->d_cell_scratch);
+                        ctx->d_cell_scratch = nullptr;
+                        ctx->cell_scratch_doubles = 0;
+                    }
+                    if (double(need) * 8.0 <= cap_gb * 1e9 && need * 8 + (size_t(2) << 30) <= free_b &&
+                        cudaMalloc(&buf, need * 8) == cudaSuccess) {
+                        ctx->owned_device.push_back(buf);
+                        ctx->d_cell_scratch = (double *)buf;
+                        ctx->cell_scratch_doubles = need;
+                    } else {
+                        cudaGetLastError();
+                        ctx->cell_scratch_refused = true;
+                    }
+                }
+                if (need > 0 && need <= ctx->cell_scratch_doubles) {
+                    A.cells = ctx->d_cells;
+                    A.n_cells = ctx->n_cells;
+                    A.scratch = ctx->d_cell_scratch;
+                }
+            }
             ProfScope prof(ctx, jac ? FEDMX_PROF_ASM_JAC : FEDMX_PROF_ASM_RES);
             int rc = ctx->plugin_launch(&A, jac ? 1 : 0, 2, (void *)ctx->stream);
-            ctx->launches++;
+            ctx->launches += A.scratch ? 2 : 1;
             if (rc) { ctx->err = "assemble: plug-in launch failed"; return FEDMX_ECUDA; }
             FEDMX_CHECK_CUDA(ctx, cudaGetLastError());
             return FEDMX_OK;
@@ -818,6 +855,7 @@ extern "C" int fedmx_plugin_load(fedmx_ctx *ctx, const char *path) {
     FEDMX_REQUIRE(ctx, nf() <= FEDMX_MAX_REFS, "fedmx_plugin_load: too many coefficient fields");
     ctx->plugin_handle = h;
     ctx->plugin_launch = launch;
+    ctx->plugin_cell_doubles = (int (*)(int))dlsym(h, "fedmx_plugin_cell_doubles");      // optional entry point
     ctx->mp.model_id = FEDMX_MODEL_PLUGIN;
     ctx->mp.n_eq = neq();
     ctx->mp.n_fields = nf();

@@ -39,6 +39,7 @@ struct SellView {
     const int32_t *inc_vp;      // neighbour vertex shared with the previous cell of the fan
     const int32_t *inc_vn;      // neighbour vertex shared with the next cell of the fan
     const uint32_t *inc_pack;   // see PACK_* below
+    const uint32_t *inc_cid;    // cell << 4 | ka << 2 | kp: the cell of the fan entry and the positions of the row's node / of vp in it
     const uint32_t *row_pack;   // [n_slices*32]: n_inc | diag_slot<<8 | bc_value_index+1 <<16 | (row touches a marked exterior facet) <<31
     // Storage row r (slice r/32, lane r%32) holds mesh node row_node[r].  The rows are ordered in spatially compact tiles
     // of FEDMX_TILE consecutive rows (recursive coordinate bisection, fedmx_topology.cu), so that one CTA of the tiled
@@ -147,6 +148,11 @@ struct fedmx_ctx {
     int64_t n_vertices = 0;      // local vertices incl. ghosts
     int64_t n_owned = 0;         // owned vertices are numbered first
     double *d_coords = nullptr;  // [n_vertices][2]
+    int32_t *d_cells = nullptr;  // [n_cells][3] local vertex indices
+    int64_t n_cells = 0;
+    double *d_cell_scratch = nullptr;   // per-cell element records of plug-in models that assemble cell-wise (row_kernel.cuh)
+    size_t cell_scratch_doubles = 0;
+    bool cell_scratch_refused = false;  // allocation failed or over the cap once: row-wise assembly from then on
     SellView sell{};
     TileView tiles{};
     std::vector<int32_t> h_row_node, h_node_row;   // storage row <-> owned node
@@ -166,6 +172,7 @@ struct fedmx_ctx {
     // run-time compiled model (form compiler plug-in)
     void *plugin_handle = nullptr;
     int (*plugin_launch)(const void *args, int jac, int minb, void *stream) = nullptr;
+    int (*plugin_cell_doubles)(int jac) = nullptr;   // optional: doubles per cell of the plug-in's cell-wise path (0: none)
     FieldRef plugin_refs[FEDMX_MAX_REFS] = {};
     double *d_nodal = nullptr;   // library-owned per-node precomputations of the model (e.g. exp(u/6))
     // Dirichlet

@@ -274,15 +274,21 @@ extern "C" int fedmx_mesh_set(fedmx_ctx *ctx, int n_eq, int64_t n_vertices, cons
     }
     const int64_t n_inc = inc_ptr[n_slices];
     std::vector<int32_t> inc_vp(n_inc, 0), inc_vn(n_inc, 0);
-    std::vector<uint32_t> inc_pack(n_inc, 0), inc_cell(n_inc, 0);
+    std::vector<uint32_t> inc_pack(n_inc, 0), inc_cell(n_inc, 0), inc_cid(n_inc, 0);
+    const bool cid_ok = n_cells < (int64_t(1) << 28);
     for (int64_t r = 0; r < NO; ++r) {
         int64_t s = r / FEDMX_SLICE, l = r % FEDMX_SLICE;
-        const std::vector<Inc> &fan = fans[row_node[r]];
+        const int32_t v = row_node[r];
+        const std::vector<Inc> &fan = fans[v];
         for (size_t m = 0; m < fan.size(); ++m) {
             int64_t e = int64_t(inc_ptr[s]) + int64_t(m) * FEDMX_SLICE + l;
             inc_vp[e] = fan[m].vp;
             inc_vn[e] = fan[m].vn;
             inc_pack[e] = fan[m].pack;
+            const int32_t *cv = h_cells + 3 * int64_t(fan[m].cell);
+            const uint32_t ka = (cv[0] == v) ? 0 : (cv[1] == v ? 1 : 2);
+            const uint32_t kp = (cv[0] == fan[m].vp) ? 0 : (cv[1] == fan[m].vp ? 1 : 2);
+            inc_cid[e] = (uint32_t(fan[m].cell) << 4) | (ka << 2) | kp;
         }
     }
 
@@ -371,6 +377,13 @@ extern "C" int fedmx_mesh_set(fedmx_ctx *ctx, int n_eq, int64_t n_vertices, cons
     if ((rc = fedmx_upload(ctx, &p32, inc_vp))) return rc; S.inc_vp = p32;
     if ((rc = fedmx_upload(ctx, &p32, inc_vn))) return rc; S.inc_vn = p32;
     if ((rc = fedmx_upload(ctx, &pu32, inc_pack))) return rc; S.inc_pack = pu32;
+    S.inc_cid = nullptr;
+    if (cid_ok) {                             // cell-wise path of the plug-in models (row_kernel.cuh)
+        if ((rc = fedmx_upload(ctx, &pu32, inc_cid))) return rc; S.inc_cid = pu32;
+        std::vector<int32_t> cv(h_cells, h_cells + 3 * int64_t(n_cells));
+        if ((rc = fedmx_upload(ctx, &ctx->d_cells, cv))) return rc;
+        ctx->n_cells = n_cells;
+    }
     if ((rc = fedmx_upload(ctx, &pu32, row_pack))) return rc; S.row_pack = pu32;
     if ((rc = fedmx_upload(ctx, &p32, row_node))) return rc; S.row_node = p32;
     if (tiles_ok) {

@@ -1,6 +1,7 @@
 // Generic row-assembly kernel of libfedmx, shared by the built-in models (fedmx_assemble.cu) and by the row kernels the
 // form compiler generates at run time (fedm_b200/formcompiler.py -> plug-in .so).  See fedmx_assemble.cu for the design.
 #pragma once
+#include <type_traits>
 #include <math.h>
 #include <stdlib.h>
 
@@ -24,6 +25,9 @@ struct AsmArgs {
     FieldRef refs[FEDMX_MAX_REFS];   // plug-in models: coefficient k of vertex v is refs[k].ptr[v*stride + offset]
     double *val;            // matrix values (may be null for residual-only)
     double *res;            // residual (may be null)
+    const int32_t *cells;   // [n_cells][3] (cell-wise path of the plug-ins)
+    int64_t n_cells;
+    double *scratch;        // per-cell element records (null: row-wise path)
     ModelParams mp;
 };
 
@@ -249,10 +253,183 @@ __global__ void __launch_bounds__(128, MINB) assemble_rows_kernel(AsmArgs A) {
 }
 
 
+// =====================================================================================================
+// Cell-wise path (models with CELLS = true: the form compiler's plug-ins)
+// =====================================================================================================
+// The generic row kernel evaluates a cell's integrand once per (row, cell) pair, i.e. three times per cell; for generated
+// forms (forward-mode AD, several exp/pow per quadrature point) that redundancy is the whole cost.  Here the work is split:
+//   1. assemble_cells_kernel: one thread per cell evaluates the element vector/tensor ONCE (Model::cell) and writes three
+//      records -- one per test vertex i: R_i[NEQ], then dR_i/dU_b for b = 0..2 (NB each) -- to A.scratch.  The scratch is
+//      SoA over blocks of 32 cells: element e of record (cell, i) at ((cell / 32) * 3 REC + i REC + e) * 32 + cell % 32, so
+//      every store of a warp covers 256 contiguous bytes (an AoS record per thread made the Jacobian variant write-bound:
+//      8-byte pieces of 32 different sectors per instruction);
+//   2. gather_rows_kernel: the row threads walk their fans in the same fixed order as the row kernel and add the records
+//      up with the same carry / single-store logic, so the scatter stays deterministic.  Rows that touch a marked exterior
+//      facet (row_pack bit 31; O(sqrt N) of them) evaluate Model::row themselves, facet integrals included.
+template <class Model, bool JAC, int MINB>
+__global__ void __launch_bounds__(128, MINB) assemble_cells_kernel(AsmArgs A) {
+    constexpr int NEQ = Model::NEQ, NF = Model::NF, NC = Model::NC;
+    constexpr int REC = JAC ? Model::REC_JAC : Model::REC_RES;
+    const int64_t c = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (c >= A.n_cells) return;
+    const int32_t i0 = __ldg(A.cells + 3 * c), i1 = __ldg(A.cells + 3 * c + 1), i2 = __ldg(A.cells + 3 * c + 2);
+    Vtx<NEQ, NF, NC> v0, v1, v2;
+    load_vertex<NEQ, NF, NC>(A, i0, v0);
+    load_vertex<NEQ, NF, NC>(A, i1, v1);
+    load_vertex<NEQ, NF, NC>(A, i2, v2);
+    Model::template cell<JAC>(A.mp, v0, v1, v2, A.scratch + (c >> 5) * (3 * REC * FEDMX_SLICE) + (c & 31));
+}
+
+// One row of the gather pass.  BOUNDARY: the row touches a marked exterior facet and evaluates Model::row itself.
+template <class Model, bool JAC, bool BOUNDARY>
+__device__ __forceinline__ void gather_row(const AsmArgs &A, int64_t row, uint32_t rp) {
+    constexpr int NEQ = Model::NEQ, NF = Model::NF, NC = Model::NC, NB = NEQ * NEQ;
+    constexpr int REC = JAC ? Model::REC_JAC : Model::REC_RES;
+    constexpr unsigned ZMASK = Model::ZERO_MASK;
+    const int64_t s = row / FEDMX_SLICE;
+    const int lane = int(row % FEDMX_SLICE);
+    const int n_inc = int(rp & 0xffu);
+    const int diag_slot = int((rp >> 8) & 0xffu);
+    const int bc = int((rp >> 16) & 0x7fffu);
+    const int bc_comp = A.mp.bc_comp;
+    const int64_t gbase = A.S.slice_ptr[s];
+    const int64_t ibase = A.S.inc_ptr[s];
+    const int32_t node = A.S.row_node[row];
+
+    double diag[NB], carry[NB], R[NEQ];
+#pragma unroll
+    for (int e = 0; e < NB; ++e) { diag[e] = 0.0; carry[e] = 0.0; }
+#pragma unroll
+    for (int k = 0; k < NEQ; ++k) R[k] = 0.0;
+
+    Vtx<NEQ, NF, NC> va;
+    if constexpr (BOUNDARY) load_vertex<NEQ, NF, NC>(A, node, va);
+    uint32_t pack = 0, cid = 0;
+    if (n_inc > 0) { pack = __ldg(A.S.inc_pack + ibase + lane); cid = __ldg(A.S.inc_cid + ibase + lane); }
+    for (int m = 0; m < n_inc; ++m) {
+        uint32_t pack1 = 0, cid1 = 0;
+        if (m + 1 < n_inc) {                                             // indices of cell m+1
+            const int64_t e = ibase + int64_t(m + 1) * FEDMX_SLICE + lane;
+            pack1 = __ldg(A.S.inc_pack + e); cid1 = __ldg(A.S.inc_cid + e);
+        }
+        double oR[NEQ], oJ0[JAC ? NB : 1], oJ1[JAC ? NB : 1], oJ2[JAC ? NB : 1];
+        if constexpr (BOUNDARY) {
+            const int64_t e = ibase + int64_t(m) * FEDMX_SLICE + lane;
+            Vtx<NEQ, NF, NC> p, n;
+            load_vertex<NEQ, NF, NC>(A, A.S.inc_vp[e], p);
+            load_vertex<NEQ, NF, NC>(A, A.S.inc_vn[e], n);
+            RowOut<NEQ> o;
+            Model::template row<JAC>(A.mp, va, p, n, PACK_MK_N(pack), PACK_MK_P(pack), o);
+#pragma unroll
+            for (int k = 0; k < NEQ; ++k) oR[k] = o.R[k];
+            if constexpr (JAC) {
+#pragma unroll
+                for (int q = 0; q < NB; ++q) { oJ0[q] = o.J[0][q]; oJ1[q] = o.J[1][q]; oJ2[q] = o.J[2][q]; }
+            }
+        } else {
+            const int ka = int((cid >> 2) & 3u), kp = int(cid & 3u), kn = 3 - ka - kp;
+            const int64_t c = int64_t(cid >> 4);
+            const double *rec = A.scratch + ((c >> 5) * (3 * REC) + ka * REC) * FEDMX_SLICE + (c & 31);
+#pragma unroll
+            for (int k = 0; k < NEQ; ++k) oR[k] = rec[k * FEDMX_SLICE];
+            if constexpr (JAC) {
+                const double *j0 = rec + (NEQ + ka * NB) * FEDMX_SLICE, *j1 = rec + (NEQ + kp * NB) * FEDMX_SLICE,
+                             *j2 = rec + (NEQ + kn * NB) * FEDMX_SLICE;
+#pragma unroll
+                for (int q = 0; q < NB; ++q) { oJ0[q] = j0[q * FEDMX_SLICE]; oJ1[q] = j1[q * FEDMX_SLICE]; oJ2[q] = j2[q * FEDMX_SLICE]; }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < NEQ; ++k) R[k] += oR[k];
+        if constexpr (JAC) {
+#pragma unroll
+            for (int q = 0; q < NB; ++q) diag[q] += oJ0[q];
+            if (PACK_FIRST(pack)) {
+#pragma unroll
+                for (int q = 0; q < NB; ++q) carry[q] = 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < NB; ++q) carry[q] += oJ1[q];
+            if (bc) zero_row<NEQ>(carry, bc_comp);
+            store_block<NEQ, ZMASK>(A, gbase, PACK_SLOT_P(pack), lane, carry);    // block (i, vp) complete: write it
+#pragma unroll
+            for (int q = 0; q < NB; ++q) carry[q] = oJ2[q];
+            if (PACK_LAST(pack)) {
+                if (bc) zero_row<NEQ>(carry, bc_comp);
+                if (PACK_CLOSED(pack)) add_block<NEQ, ZMASK>(A, gbase, PACK_SLOT_N(pack), lane, carry);
+                else store_block<NEQ, ZMASK>(A, gbase, PACK_SLOT_N(pack), lane, carry);
+            }
+        }
+        pack = pack1;
+        cid = cid1;
+    }
+    if (bc) {
+        const double g = A.mp.bc_values[bc - 1];
+#pragma unroll
+        for (int k = 0; k < NEQ; ++k)
+            if (k == bc_comp) R[k] = __ldg(A.x + int64_t(NEQ) * node + k) - g;
+        if (JAC) {
+            zero_row<NEQ>(diag, bc_comp);
+#pragma unroll
+            for (int k = 0; k < NEQ; ++k)
+                if (k == bc_comp) diag[k * NEQ + k] = 1.0;
+        }
+    }
+    if (JAC && A.mp.ident_zeros) {                  // see assemble_rows_kernel
+#pragma unroll
+        for (int k = 0; k < NEQ; ++k) {
+            bool zero = true;
+#pragma unroll
+            for (int l = 0; l < NEQ; ++l) zero = zero && diag[k * NEQ + l] == 0.0;
+#pragma unroll
+            for (int l = 0; l < NEQ; ++l)
+                if (l == k && zero) diag[k * NEQ + l] = 1.0;
+        }
+    }
+    if (JAC) store_block<NEQ, ZMASK>(A, gbase, diag_slot, lane, diag);
+    if (A.res) {
+#pragma unroll
+        for (int k = 0; k < NEQ; ++k) A.res[int64_t(NEQ) * node + k] = R[k];
+    }
+}
+
+template <class Model, bool JAC>
+__device__ __noinline__ void gather_boundary_row(const AsmArgs &A, int64_t row, uint32_t rp) {
+    gather_row<Model, JAC, true>(A, row, rp);
+}
+
+template <class Model, bool JAC, int MINB>
+__global__ void __launch_bounds__(128, MINB) gather_rows_kernel(const __grid_constant__ AsmArgs A) {
+    const int64_t row = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (row >= A.S.n_rows) return;
+    const uint32_t rp = A.S.row_pack[row];
+    if (rp >> 31) gather_boundary_row<Model, JAC>(A, row, rp);
+    else gather_row<Model, JAC, false>(A, row, rp);
+}
+
+template <class Model, class = void>
+struct ModelHasCells { static constexpr bool value = false; };
+template <class Model>
+struct ModelHasCells<Model, std::enable_if_t<Model::CELLS>> { static constexpr bool value = true; };
+
 // Launch helper shared by the built-in dispatch and by plug-ins.
 template <class Model>
 inline void launch_rows(const AsmArgs &A, bool jac, int minb, cudaStream_t stream) {
     const int threads = 128;
+    if constexpr (ModelHasCells<Model>::value) {
+        if (A.scratch && A.cells && A.S.inc_cid && (!jac || Model::CELLS_JAC)) {
+            const unsigned cblocks = unsigned((A.n_cells + threads - 1) / threads);
+            const unsigned rblocks = unsigned((A.S.n_rows + threads - 1) / threads);
+            if (jac) {
+                assemble_cells_kernel<Model, true, Model::CELL_MINB><<<cblocks, threads, 0, stream>>>(A);
+                gather_rows_kernel<Model, true, 4><<<rblocks, threads, 0, stream>>>(A);
+            } else {
+                assemble_cells_kernel<Model, false, 4><<<cblocks, threads, 0, stream>>>(A);
+                gather_rows_kernel<Model, false, 4><<<rblocks, threads, 0, stream>>>(A);
+            }
+            return;
+        }
+    }
     const int64_t rows = A.S.n_slices * FEDMX_SLICE;
     const unsigned blocks = unsigned((rows + threads - 1) / threads);
     if (jac) {

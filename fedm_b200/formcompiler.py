@@ -224,6 +224,7 @@ class CompiledForm:
         self.interps, self._interp_ids = [], {}
         self._varies = {}
         self._skeys = {}
+        self._deps = {}
         self.used_u, self.used_gu, self.used_fval, self.used_gf = set(), set(), set(), set()
         groups = {}
         self.facet_data = None
@@ -304,6 +305,19 @@ class CompiledForm:
             self._varies[k] = v
         return self._varies[k]
 
+    def deps(self, e):
+        """Components of the unknown an expression depends on (a superset of what the emitted C++ type carries)."""
+        k = id(e)
+        if k not in self._deps:
+            if isinstance(e, U.Field):
+                v = frozenset([e.comp]) if e.fn is self.unknown else frozenset()
+            elif isinstance(e, U.Interp):
+                v = frozenset()
+            else:
+                v = frozenset().union(*[self.deps(ch) for ch in e.children()]) if e.children() else frozenset()
+            self._deps[k] = v
+        return self._deps[k]
+
     def param_values(self):
         return np.array([float(p.getter()) for p in self.params] + [0.0], dtype=np.float64)
 
@@ -330,19 +344,46 @@ class CompiledForm:
                 if not zero(fy):
                     parts.append(f"({em.emit(fy)[0]}) * ga_z")
                 acc.append(f"R[{k}] = R[{k}] + ({' + '.join(parts)}) * W;")
-            body = em.end_scope() + acc
+            scope = em.end_scope()
+            # cell-wise variant: one quadrature loop per equation k (only 5 dual accumulators live at a time: the integrand
+            # against the three test functions, S_i += s W l_i, and its flux part F += f W, which meets grad v_i after the loop)
+            per_k = []
+            if kind == "dx":
+                for k, (s, fx, fy) in enumerate(split):
+                    if zero(s) and zero(fx) and zero(fy):
+                        continue
+                    em.begin_scope()
+                    lines = []
+                    if not zero(s):
+                        code = em.emit(s)[0]
+                        lines += [f"const auto sW = ({code}) * W;", "S0 = S0 + sW * l0;", "S1 = S1 + sW * l1;", "S2 = S2 + sW * l2;"]
+                    if not zero(fx):
+                        lines.append(f"FX = FX + ({em.emit(fx)[0]}) * W;")
+                    if not zero(fy):
+                        lines.append(f"FY = FY + ({em.emit(fy)[0]}) * W;")
+                    mask = 0
+                    for e in (s, fx, fy):
+                        for c in self.deps(e):
+                            mask |= 1 << c
+                    per_k.append((k, mask, not zero(fx), not zero(fy), em.end_scope() + lines))
             if kind == "dx":
                 pts, w = triangle_rule(deg)
                 tables.append(f"static __device__ __constant__ double QC{gi}[{len(w)}][4] = {{" +
                               ", ".join("{" + ", ".join(repr(float(v)) for v in (*p, ww)) + "}" for p, ww in zip(pts, w)) + "};")
-                cell_blocks.append((gi, len(w), body))
+                cell_blocks.append((gi, len(w), scope + acc, per_k))
             else:
                 t, w = facet_rule(deg)
                 tables.append(f"static __device__ __constant__ double QF{gi}[{len(w)}][2] = {{" +
                               ", ".join("{" + f"{float(a)!r}, {float(b)!r}" + "}" for a, b in zip(t, w)) + "};")
-                facet_blocks.append((gi, sid, len(w), body))
+                facet_blocks.append((gi, sid, len(w), scope + acc))
 
         nf = len(self.fields)
+        rec_jac = (neq + 3 * neq * neq + 1) // 2 * 2          # doubles per (cell, test vertex) record, 16-byte aligned
+        rec_res = (neq + 1) // 2 * 2
+        # cell-wise evaluation (row_kernel.cuh) pays when the integrand is expensive and the 3 n_eq (1 + 3 n_eq) accumulators
+        # of a cell still fit the register file
+        cost = sum(nq * len(body) for _, nq, body, _ in cell_blocks)
+        self.cellwise = bool(cell_blocks) and neq <= 3 and cost >= 60
         L = []
         L.append("// Generated by fedm_b200/formcompiler.py -- do not edit.")
         L.append('#include "row_kernel.cuh"')
@@ -355,35 +396,40 @@ class CompiledForm:
         L.append("    static constexpr int MINB = 2, MINB_RES = 2;")
         L.append("    static constexpr unsigned ZERO_MASK = 0;")
         L.append(f"    static constexpr int NEQ = {neq};\n    static constexpr int NF = {nf};\n    static constexpr int NC = 0;")
+        L.append(f"    static constexpr bool CELLS = {'true' if self.cellwise else 'false'};")
+        cells_jac = os.environ.get("FEDMX_JIT_CELLS_JAC", "1") != "0"       # tuning knob: Jacobian launches row-wise
+        L.append(f"    static constexpr bool CELLS_JAC = {'true' if cells_jac else 'false'};")
+        L.append(f"    static constexpr int REC_JAC = {rec_jac}, REC_RES = {rec_res}, CELL_MINB = {int(os.environ.get('FEDMX_JIT_CELL_MINB', '2'))};")
         L.append(f"    typedef Vtx<{neq}, {nf}, 0> V;")
-        L.append("    template <bool JAC>")
-        L.append(f"    static __device__ __noinline__ void row(const ModelParams &mp, const V &a, const V &p, const V &n, uint32_t mk_ap, uint32_t mk_an, RowOut<{neq}> &o) {{")
         if neq > 16:
             raise NotImplementedError("more than 16 unknown components")
-        L.append(f"        constexpr unsigned ALL = JAC ? {(1 << neq) - 1}u : 0u;   // residual-only: the same code on value-only duals")
-        L.append("        const double e1r = p.r - a.r, e1z = p.z - a.z, e2r = n.r - a.r, e2z = n.z - a.z;")
-        L.append("        const double det = e1r * e2z - e1z * e2r, inv = 1.0 / det, adet = fabs(det);")
-        L.append("        const double g_r[3] = {-(e2z - e1z) * inv, e2z * inv, -e1z * inv};")
-        L.append("        const double g_z[3] = {-(e1r - e2r) * inv, -e2r * inv, e1r * inv};")
-        L.append("        const double ga_r = g_r[0], ga_z = g_z[0];")
-        L.append("        // FFC's reference cell lists the vertices by ascending index: ranks of (a,p,n) in that order")
-        L.append("        const int ra = (a.id > p.id) + (a.id > n.id), rp = (p.id > a.id) + (p.id > n.id), rn = 3 - ra - rp;")
-        for k in sorted(self.used_gu):
-            for i, g in enumerate(("g_r", "g_z")):
-                L.append(f"        const auto gu{k}_{i} = cd_seed<JAC ? {1 << k}u : 0u>(a.u[{k}] * {g}[0] + p.u[{k}] * {g}[1] + "
-                         f"n.u[{k}] * {g}[2], {g}[0], {g}[1], {g}[2]);")
-        for j in sorted(self.used_gf):
-            for i, g in enumerate(("g_r", "g_z")):
-                L.append(f"        const double gf{j}_{i} = a.f[{j}] * {g}[0] + p.f[{j}] * {g}[1] + n.f[{j}] * {g}[2];")
-        # nodal values of interpolated Expressions (reference vertex order = ascending index, harmless for symmetric node sets)
-        for k, ip in enumerate(self.interps):
-            nodes = _P_NODES[ip.degree]
-            L.append(f"        double nv{k}[{len(nodes)}];")
-            for b, w in enumerate(nodes):
-                L.append(f"        nv{k}[{b}] = interp_fn{k}({w[0]!r} * a.r + {w[1]!r} * p.r + {w[2]!r} * n.r, {w[0]!r} * a.z + {w[1]!r} * p.z + {w[2]!r} * n.z, mp);")
-        L += ["        " + ln for ln in em.cell_lines]
-        L.append(f"        CD<ALL> R[{neq}];")
-        L.append(f"        for (int k = 0; k < {neq}; ++k) R[k] = cd_zero<ALL>();")
+
+        def cell_prelude():
+            """Geometry, gradients of the unknowns (seeded duals) and of the coefficient fields, cell-constant sub-expressions:
+            shared by row() (a = the row's vertex) and cell() (a, p, n = the cell's vertices)."""
+            P = []
+            P.append(f"        constexpr unsigned ALL = JAC ? {(1 << neq) - 1}u : 0u;   // residual-only: the same code on value-only duals")
+            P.append("        const double e1r = p.r - a.r, e1z = p.z - a.z, e2r = n.r - a.r, e2z = n.z - a.z;")
+            P.append("        const double det = e1r * e2z - e1z * e2r, inv = 1.0 / det, adet = fabs(det);")
+            P.append("        const double g_r[3] = {-(e2z - e1z) * inv, e2z * inv, -e1z * inv};")
+            P.append("        const double g_z[3] = {-(e1r - e2r) * inv, -e2r * inv, e1r * inv};")
+            P.append("        // FFC's reference cell lists the vertices by ascending index: ranks of (a,p,n) in that order")
+            P.append("        const int ra = (a.id > p.id) + (a.id > n.id), rp = (p.id > a.id) + (p.id > n.id), rn = 3 - ra - rp;")
+            for k in sorted(self.used_gu):
+                for i, g in enumerate(("g_r", "g_z")):
+                    P.append(f"        const auto gu{k}_{i} = cd_seed<JAC ? {1 << k}u : 0u>(a.u[{k}] * {g}[0] + p.u[{k}] * {g}[1] + "
+                             f"n.u[{k}] * {g}[2], {g}[0], {g}[1], {g}[2]);")
+            for j in sorted(self.used_gf):
+                for i, g in enumerate(("g_r", "g_z")):
+                    P.append(f"        const double gf{j}_{i} = a.f[{j}] * {g}[0] + p.f[{j}] * {g}[1] + n.f[{j}] * {g}[2];")
+            # nodal values of interpolated Expressions (reference vertex order = ascending index, harmless for symmetric node sets)
+            for k, ip in enumerate(self.interps):
+                nodes = _P_NODES[ip.degree]
+                P.append(f"        double nv{k}[{len(nodes)}];")
+                for b, w in enumerate(nodes):
+                    P.append(f"        nv{k}[{b}] = interp_fn{k}({w[0]!r} * a.r + {w[1]!r} * p.r + {w[2]!r} * n.r, {w[0]!r} * a.z + {w[1]!r} * p.z + {w[2]!r} * n.z, mp);")
+            P += ["        " + ln for ln in em.cell_lines]
+            return P
 
         def point_prelude(l0, l1, l2, indent):
             P = []
@@ -398,7 +444,14 @@ class CompiledForm:
                 P.append(f"const double ip{k} = " + " + ".join(f"({b}) * nv{k}[{i}]" for i, b in enumerate(basis)) + ";")
             return [indent + ln for ln in P]
 
-        for gi, nq, body in cell_blocks:
+        # ---- row(): row `a` of the element tensor of cell (a, p, n), cell and exterior-facet integrals
+        L.append("    template <bool JAC>")
+        L.append(f"    static __device__ __noinline__ void row(const ModelParams &mp, const V &a, const V &p, const V &n, uint32_t mk_ap, uint32_t mk_an, RowOut<{neq}> &o) {{")
+        L += cell_prelude()
+        L.append("        const double ga_r = g_r[0], ga_z = g_z[0];")
+        L.append(f"        CD<ALL> R[{neq}];")
+        L.append(f"        for (int k = 0; k < {neq}; ++k) R[k] = cd_zero<ALL>();")
+        for gi, nq, body, _ in cell_blocks:
             L.append(f"        for (int q = 0; q < {nq}; ++q) {{")
             L.append(f"            const double l0 = QC{gi}[q][ra], l1 = QC{gi}[q][rp], l2 = QC{gi}[q][rn];")
             L.append(f"            const double W = QC{gi}[q][3] * adet, LA = l0;")
@@ -429,11 +482,58 @@ class CompiledForm:
         L.append(f"            if constexpr (JAC) for (int bb = 0; bb < 3; ++bb) for (int l = 0; l < {neq}; ++l) o.J[bb][k * {neq} + l] = R[k].d[3 * l + bb];")
         L.append("        }")
         L.append("    }")
+        # ---- cell(): the cell integrals of all three rows at once, written as three records (row_kernel.cuh, cell-wise path)
+        L.append("    template <bool JAC>")
+        L.append("    static __device__ __forceinline__ void cell(const ModelParams &mp, const V &a, const V &p, const V &n, double *rec) {")
+        if self.cellwise:
+            L += cell_prelude()
+            L.append("        constexpr int REC = JAC ? REC_JAC : REC_RES, RS = FEDMX_SLICE;   // record element stride (see row_kernel.cuh)")
+            done = set()
+            for gi, nq, _, per_k in cell_blocks:
+                for k, mask, has_fx, has_fy, body in per_k:
+                    if k in done:
+                        raise NotImplementedError("cell-wise path: several cell quadrature rules for one equation")
+                    done.add(k)
+                    L.append("        {")
+                    L.append(f"            constexpr unsigned MK = JAC ? {mask}u : 0u;       // components equation {k} depends on")
+                    L.append("            CD<MK> S0 = cd_zero<MK>(), S1 = cd_zero<MK>(), S2 = cd_zero<MK>(), FX = cd_zero<MK>(), FY = cd_zero<MK>();")
+                    L.append(f"            for (int q = 0; q < {nq}; ++q) {{")
+                    L.append(f"                const double l0 = QC{gi}[q][ra], l1 = QC{gi}[q][rp], l2 = QC{gi}[q][rn];")
+                    L.append(f"                const double W = QC{gi}[q][3] * adet;")
+                    L += point_prelude("l0", "l1", "l2", "                ")
+                    L += ["                " + ln for ln in body]
+                    L.append("            }")
+                    for i in range(3):
+                        terms = [f"S{i}"] + ([f"FX * g_r[{i}]"] if has_fx else []) + ([f"FY * g_z[{i}]"] if has_fy else [])
+                        L.append(f"            const CD<MK> T{i} = {' + '.join(terms)};")
+                        L.append(f"            rec[({i} * REC + {k}) * RS] = T{i}.v;")
+                        L.append("            if constexpr (JAC) {")
+                        for bb in range(3):
+                            for l in range(neq):
+                                if mask >> l & 1:
+                                    rank = bin(mask & ((1 << l) - 1)).count("1")
+                                    val = f"T{i}.d[{3 * rank + bb}]"
+                                else:
+                                    val = "0.0"
+                                L.append(f"                rec[({i} * REC + {neq + bb * neq * neq + k * neq + l}) * RS] = {val};")
+                        L.append("            }")
+                    L.append("        }")
+            for k in range(neq):
+                if k not in done:                       # equation without a cell integral: zero records
+                    for i in range(3):
+                        L.append(f"        rec[({i} * REC + {k}) * RS] = 0.0;")
+                        L.append("        if constexpr (JAC) {")
+                        for bb in range(3):
+                            for l in range(neq):
+                                L.append(f"            rec[({i} * REC + {neq + bb * neq * neq + k * neq + l}) * RS] = 0.0;")
+                        L.append("        }")
+        L.append("    }")
         L.append("};")
         L.append("}  // namespace")
         L.append('extern "C" int fedmx_plugin_neq() { return JitModel::NEQ; }')
         L.append('extern "C" int fedmx_plugin_nf() { return JitModel::NF; }')
         L.append('extern "C" int fedmx_plugin_args_size() { return int(sizeof(AsmArgs)); }')
+        L.append('extern "C" int fedmx_plugin_cell_doubles(int jac) { return JitModel::CELLS ? 3 * (jac ? JitModel::REC_JAC : JitModel::REC_RES) : 0; }')
         L.append('extern "C" int fedmx_plugin_launch(const void *args, int jac, int minb, void *stream) {')
         L.append("    launch_rows<JitModel>(*(const AsmArgs *)args, jac != 0, minb, (cudaStream_t)stream);")
         L.append("    return cudaGetLastError() == cudaSuccess ? 0 : 1;")

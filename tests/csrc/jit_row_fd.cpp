@@ -8,7 +8,7 @@ int main() {
     typedef JitModel::V V;
     std::mt19937 g(3); std::uniform_real_distribution<double> U(0, 1);
     ModelParams mp; for (int i = 0; i < FEDMX_MAX_PARAMS; ++i) mp.p[i] = 0.5 + U(g);
-    int bad = 0; double worst = 0.0;
+    int bad = 0, cells_checked = 0; double worst = 0.0;
     for (int trial = 0; trial < 8; ++trial) {
         V v[3];
         const double xy[3][2] = {{0.1, 0.2}, {0.4, 0.25}, {0.2, 0.6}};
@@ -22,6 +22,29 @@ int main() {
         JitModel::row<true>(mp, v[0], v[1], v[2], m1, m2, o);
         JitModel::row<false>(mp, v[0], v[1], v[2], m1, m2, o0);
         for (int k = 0; k < NEQ; ++k) if (o.R[k] != o0.R[k]) { printf("residual differs k %d\n", k); ++bad; }
+        if (JitModel::CELLS) {
+            // cell-wise variant: record i of cell(v0, v1, v2) == row(a = v_i, p = v_j, n = v_k) without facet terms
+            constexpr int NB = NEQ * NEQ, RJ = JitModel::REC_JAC, RR = JitModel::REC_RES;
+            constexpr int RS = FEDMX_SLICE;                        // record element stride
+            static double rec[3 * RJ * RS], rec0[3 * RR * RS];
+            JitModel::cell<true>(mp, v[0], v[1], v[2], rec);
+            JitModel::cell<false>(mp, v[0], v[1], v[2], rec0);
+            for (int i = 0; i < 3; ++i) {
+                const int j = (i + 1) % 3, k3 = (i + 2) % 3, perm[3] = {i, j, k3};
+                RowOut<NEQ> r;
+                JitModel::row<true>(mp, v[i], v[j], v[k3], 0, 0, r);
+                for (int k = 0; k < NEQ; ++k) {
+                    double scale = fabs(r.R[k]);
+                    for (int b = 0; b < 3; ++b) for (int l = 0; l < NEQ; ++l) scale = std::max(scale, fabs(r.J[b][k * NEQ + l]));
+                    if (fabs(rec[(i * RJ + k) * RS] - r.R[k]) > 1e-11 * scale || rec0[(i * RR + k) * RS] != rec[(i * RJ + k) * RS]) { printf("cell R differs i %d k %d\n", i, k); ++bad; }
+                    for (int b = 0; b < 3; ++b) for (int l = 0; l < NEQ; ++l) {
+                        const double c = rec[(i * RJ + NEQ + perm[b] * NB + k * NEQ + l) * RS];
+                        if (fabs(c - r.J[b][k * NEQ + l]) > 1e-11 * scale) { printf("cell J differs i %d k %d b %d l %d: %g vs %g\n", i, k, b, l, c, r.J[b][k * NEQ + l]); ++bad; }
+                    }
+                }
+            }
+            ++cells_checked;
+        }
         for (int k = 0; k < NEQ; ++k) {
             double jmax = 0.0;
             for (int b = 0; b < 3; ++b) for (int l = 0; l < NEQ; ++l) jmax = std::max(jmax, fabs(o.J[b][k * NEQ + l]));
@@ -40,6 +63,6 @@ int main() {
             }
         }
     }
-    printf("worst %g bad %d\n", worst, bad);
+    printf("worst %g cellwise %d bad %d\n", worst, cells_checked, bad);
     return bad != 0;
 }

@@ -9,6 +9,7 @@
 #define __forceinline__ inline
 using std::exp; using std::sqrt; using std::log; using std::pow; using std::fabs;
 #define FEDMX_MAX_PARAMS 128
+#define FEDMX_SLICE 32
 struct ModelParams { double p[FEDMX_MAX_PARAMS]; };
 struct AsmArgs { int x; };
 typedef void *cudaStream_t;

@@ -15,6 +15,7 @@ import dolfin
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 4
 times = []
+asm = {}
 orig = dolfin.PETScSNESSolver.solve
 
 
@@ -24,6 +25,19 @@ def timed_solve(self, problem, x):
     out = orig(self, problem, x)
     torch.cuda.synchronize()
     times.append((time.time() - t0, out[0]))
+    if len(times) == steps:                                      # last solve: time the generated assembly kernels alone
+        prob = next(iter(self._compiled.values()))[1]
+        xt = prob._x_local if prob.local is not None else x.function.vector().store.t
+        for name, fn in (("jacobian", lambda: prob.hot.jacobian(xt, 1.0, 1.0)), ("residual", lambda: prob.hot.residual(xt, 1.0, 1.0))):
+            fn()
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            torch.cuda.synchronize()
+            ev[0].record()
+            for _ in range(10):
+                fn()
+            ev[1].record()
+            torch.cuda.synchronize()
+            asm[name] = ev[0].elapsed_time(ev[1]) / 10
     return out
 
 
@@ -38,4 +52,5 @@ dof = 3 * (n + 1) ** 2
 warm = [t for t, _ in times[1:]] or [times[0][0]]
 print(f"script path, n={n} ({dof} DOF): total {total:.1f} s (set-up, JIT load, AMG hierarchy, {len(times)} solves); "
       f"solve calls {[round(t * 1e3, 1) for t, _ in times]} ms, Newton its {[k for _, k in times]}; "
-      f"warm solve {1e3 * sum(warm) / len(warm):.1f} ms -> {len(warm) / sum(warm):.1f} solves/s", flush=True)
+      f"warm solve {1e3 * sum(warm) / len(warm):.1f} ms -> {len(warm) / sum(warm):.1f} solves/s; generated assembly kernels "
+      f"(incl. block-Jacobi update) {', '.join(f'{k} {v:.2f} ms' for k, v in asm.items())}", flush=True)
