@@ -126,7 +126,11 @@ int fedmx_model_set(fedmx_ctx *ctx, int model_id, int n_params, const double *h_
  * row kernel (fedm_b200/csrc/row_kernel.cuh), nvcc builds a plug-in .so, fedmx_plugin_load binds it to the context and
  * fedmx_plugin_set_field tells the kernel where coefficient k lives (component `offset` of a node-interleaved device
  * vector with `stride` components).  Scalar parameters (dt, dt_old, Constants ...) go through fedmx_model_set(
- * FEDMX_MODEL_PLUGIN, n, values) before every solve. */
+ * FEDMX_MODEL_PLUGIN, n, values) before every solve.
+ * Entry points the plug-in .so exports (checked by fedmx_plugin_load): fedmx_plugin_neq(), fedmx_plugin_nf(),
+ * fedmx_plugin_args_size() (must equal the library's AsmArgs), fedmx_plugin_launch(args, jac, minb, stream), and optionally
+ * fedmx_plugin_cell_doubles(jac): > 0 = the plug-in has the cell-wise path (every cell evaluated once into that many doubles
+ * of library-owned scratch per cell, rows gather; row_kernel.cuh) and the library allocates the scratch on first use. */
 int fedmx_plugin_load(fedmx_ctx *ctx, const char *so_path);
 int fedmx_plugin_set_field(fedmx_ctx *ctx, int k, const double *d_ptr, int stride, int offset);
 
