@@ -383,7 +383,7 @@ class CompiledForm:
         # cell-wise evaluation (row_kernel.cuh) pays when the integrand is expensive and the 3 n_eq (1 + 3 n_eq) accumulators
         # of a cell still fit the register file
         cost = sum(nq * len(body) for _, nq, body, _ in cell_blocks)
-        self.cellwise = bool(cell_blocks) and neq <= 3 and cost >= 60
+        self.cellwise = len(cell_blocks) == 1 and neq <= 3 and cost >= 60
         L = []
         L.append("// Generated by fedm_b200/formcompiler.py -- do not edit.")
         L.append('#include "row_kernel.cuh"')
