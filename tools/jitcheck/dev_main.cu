@@ -1,5 +1,9 @@
 #include FORM
 #include "harness.inc"
+__global__ void run_cells(const Case *cs, ModelParams mp, double *sc, int n) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x; if (t >= n) return;
+    if constexpr (JitModel::CELLS) JitModel::cell<true>(mp, cs[t].v[0], cs[t].v[1], cs[t].v[2], CELL_REC(sc, t));
+}
 __global__ void run(const Case *cs, ModelParams mp, double *out, int n) {
     constexpr int NEQ = JitModel::NEQ;
     int t = blockIdx.x * blockDim.x + threadIdx.x; if (t >= n) return;
@@ -18,5 +22,14 @@ int main(int argc, char **argv) {
     std::vector<double> h(cs.size() * kPer);
     cudaError_t e = cudaMemcpy(h.data(), o, h.size() * 8, cudaMemcpyDeviceToHost);
     printf("cuda: %s\n", cudaGetErrorString(e));
-    FILE *f = fopen(argv[1], "wb"); fwrite(h.data(), 8, h.size(), f); fclose(f);
+    FILE *f = fopen(argv[1], "wb"); fwrite(h.data(), 8, h.size(), f);
+    if (JitModel::CELLS) {
+        std::vector<double> sc((cs.size() + 31) / 32 * kCellBlock, 0.0);
+        double *dsc; cudaMalloc(&dsc, sc.size() * 8); cudaMemset(dsc, 0, sc.size() * 8);
+        run_cells<<<4, 64>>>(d, mp, dsc, 256);
+        e = cudaMemcpy(sc.data(), dsc, sc.size() * 8, cudaMemcpyDeviceToHost);
+        printf("cuda (cells): %s\n", cudaGetErrorString(e));
+        fwrite(sc.data(), 8, sc.size(), f);
+    }
+    fclose(f);
 }
