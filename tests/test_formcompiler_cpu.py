@@ -148,6 +148,27 @@ def test_generated_rows_have_the_exact_jacobian_of_their_residual(tmp_path):
         assert "bad 0" in out, (f.name, out[-2000:])
 
 
+def test_cellwise_path_is_generated_only_where_it_pays():
+    """Cell-wise assembly (row_kernel.cuh) is emitted for expensive integrands (the ToF form: 25 quadrature points with exp) and
+    not for a Poisson residual; the plug-in reports its scratch need through fedmx_plugin_cell_doubles."""
+    from fedm_b200 import formcompiler as fc
+    df.parameters["form_compiler"]["quadrature_degree"] = None
+    mesh = df.RectangleMesh(df.Point(0, 0), df.Point(1, 1), 2, 2)
+    form, u_new = _tof_form(mesh)
+    tof = fc.CompiledForm(form, u_new, None)
+    assert tof.cellwise and "static constexpr bool CELLS = true;" in tof.source
+    assert "REC_JAC = 4, REC_RES = 2" in tof.source                      # n_eq + 3 n_eq^2 = 4 doubles per (cell, test vertex)
+    assert "fedmx_plugin_cell_doubles" in tof.source and "FX = FX + " in tof.source
+    V = df.FunctionSpace(mesh, "P", 1)
+    u, v = df.TrialFunction(V), df.TestFunction(V)
+    phi = df.Function(V)
+    poisson = fc.CompiledForm(df.action(F.weak_form_Poisson_equation(df.dx, u, v, df.Constant(3.0)), phi), phi, None)
+    assert not poisson.cellwise and "static constexpr bool CELLS = false;" in poisson.source
+    # dependency masks: every sub-expression of the scalar ToF form can only depend on component 0
+    for it in form.integrals:
+        assert tof.deps(it.integrand) <= frozenset([0])
+
+
 def _write_dolfin_xml(path, coords, cells):
     lines = ['<?xml version="1.0"?>', '<dolfin xmlns:dolfin="http://fenicsproject.org">', '  <mesh celltype="triangle" dim="2">',
              f'    <vertices size="{len(coords)}">']
