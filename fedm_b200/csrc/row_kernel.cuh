@@ -412,7 +412,11 @@ struct ModelHasCells { static constexpr bool value = false; };
 template <class Model>
 struct ModelHasCells<Model, std::enable_if_t<Model::CELLS>> { static constexpr bool value = true; };
 
-// Launch helper shared by the built-in dispatch and by plug-ins.
+// Launch helper shared by the built-in dispatch and by plug-ins.  (Host emulation builds -- tests/csrc/cuda_emul, where a
+// kernel is a plain function -- bring their own sequential launcher with the same dispatch.)
+#ifdef FEDMX_HOST_EMULATION
+#include "emul_launch.h"
+#else
 template <class Model>
 inline void launch_rows(const AsmArgs &A, bool jac, int minb, cudaStream_t stream) {
     const int threads = 128;
@@ -447,5 +451,6 @@ inline void launch_rows(const AsmArgs &A, bool jac, int minb, cudaStream_t strea
         else assemble_rows_kernel<Model, false, 2><<<blocks, threads, 0, stream>>>(A);
     }
 }
+#endif
 
 }  // namespace
